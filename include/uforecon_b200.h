@@ -1,0 +1,206 @@
+/*
+ * uforecon_b200.h - C ABI of the B200-native per-ray rendering hot path of UFORecon.
+ *
+ * The reference (Youngju-Na/UFORecon) is pure Python/PyTorch and has no FFI: the boundary this
+ * library replaces is the Python method
+ *
+ *     UFORecon.infer(batch, ray_idx, source_imgs_feat, feature_volume, extract_geometry=True,
+ *                    match_feature, ...)  ->  (srdf, points_x_all, depth, rgb)
+ *                                                          code1/model.py:393-478
+ *
+ * as called per ray chunk by UFORecon.extract_geometry (code1/model.py:814-823), plus the
+ * cost-volume build inside DepthNet.forward (code1/encoder_utils/fmt/TransMVSNet.py:61-100).
+ * Each entry point below cites the reference code whose work it performs.  INTEGRATION.md shows
+ * the ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative UFO_E* code on failure; ufo_last_error()
+ *     returns a thread-local message.  No exceptions or torch types cross this boundary.
+ *   - pointers marked [dev] are device pointers (fp32 unless stated), [host] are host pointers.
+ *   - all tensors are contiguous in the reference's own layouts (NCHW / NCDHW), batch dim B=1
+ *     squeezed; the library repacks what it needs into its own buffers (owned by the handle).
+ *   - calls are asynchronous on the supplied cudaStream_t (passed as void*) except where noted;
+ *     handles are bound to the CUDA device that was current at creation.
+ *   - there is no CPU fallback: without a CUDA device every call fails with UFO_ENODEVICE.
+ */
+#ifndef UFORECON_B200_H_
+#define UFORECON_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UFO_ABI_VERSION 1
+#define UFO_MAX_VIEWS 10
+#define UFO_N_STAGES 3
+#define UFO_N_COARSE 64 /* --test_sample_coarse, main.py:73 */
+#define UFO_N_FINE 64   /* --test_sample_fine,   main.py:74 */
+#define UFO_N_SAMPLES (UFO_N_COARSE + UFO_N_FINE)
+
+enum {
+  UFO_OK = 0,
+  UFO_EINVAL = -1,    /* bad argument / unsupported configuration */
+  UFO_ENODEVICE = -2, /* no CUDA device / wrong architecture      */
+  UFO_ECUDA = -3,     /* CUDA runtime error (message in ufo_last_error) */
+  UFO_ENOMEM = -4
+};
+
+/* Transformer arithmetic of ufo_render_rays. */
+enum {
+  UFO_MODE_FP32 = 0, /* CUDA-core fp32 everywhere (parity: 1e-5 relative)                        */
+  UFO_MODE_TC = 1    /* BF16 operands / FP32 accumulate on tcgen05 tensor cores for the GEMMs    */
+};
+
+typedef struct UfoScene UfoScene;     /* one view set: repacked source tensors + cameras        */
+typedef struct UfoWeights UfoWeights; /* packed ray_transformer.* / deviation_network weights   */
+
+/* Inputs of infer() that describe one view set.  Spec: DtuFitSparse.__getitem__
+ * (code1/dataset/dtu_test_sparse.py:382-436) + the encoder outputs assembled in
+ * extract_geometry (code1/model.py:777-808). */
+typedef struct {
+  int32_t n_views;        /* NV, 2..UFO_MAX_VIEWS                                   */
+  int32_t img_h, img_w;   /* H, W of source images == ray grid                      */
+  int32_t feat_h, feat_w; /* h, w of the stage-1 feature / match maps (H/4, W/4)     */
+  const float* source_imgs;  /* [dev] batch['source_imgs'][0]      [NV,3,H,W]           */
+  const float* img_feats;    /* [dev] source_imgs_feat[0]          [NV,32,h,w]          */
+  const float* depth_info;   /* [dev] batch['depth_info'][0]       [NV,H,W]             */
+  const float* match_feats;  /* [dev] match_feature[0][0]          [NV,(NV-1)*32,h,w]   */
+  const float* vol_feat[UFO_N_STAGES];   /* [dev] feature_volume[stage]['feature_volume'] [NV,8,D,hs,ws] */
+  const float* vol_weight[UFO_N_STAGES]; /* [dev] feature_volume[stage]['weight_volume']  [NV,1,D,hs,ws] */
+  int32_t vol_d[UFO_N_STAGES], vol_h[UFO_N_STAGES], vol_w[UFO_N_STAGES];
+  const float* source_poses;     /* [host] batch['source_poses'][0]      [NV,4,4] world->NDC */
+  const float* source_poses_inv; /* [host] batch['source_poses_inv'][0]  [NV,4,4]            */
+  const float* ref_pose_inv;     /* [host] batch['ref_pose_inv'][0]      [4,4]               */
+  const float* w2cs;             /* [host] batch['w2cs'][0]              [NV,4,4]            */
+  const float* near_fars;        /* [host] batch['near_fars'][0]         [NV,2]              */
+  const float* ray_o;            /* [host] batch['ray_o'][0]             [3]                 */
+  const float* ray_d;            /* [dev]  batch['ray_d'][0]             [3,H*W]             */
+  const float* cam_ray_d;        /* [dev]  batch['cam_ray_d'][0]         [3,H*W]             */
+} UfoSceneDesc;
+
+/* Hot-path block of the checkpoint state dict; all [host] fp32, torch layout
+ * ([out,in] for Linear weights).  Reference modules: code1/ray_transformer.py:127-163,
+ * code1/attention/transformer.py:17-33, code1/encoder_utils/single_variance_network.py:8. */
+typedef struct {
+  const float *q, *k, *v, *merge; /* [d,d]   */
+  const float *mlp0;              /* [2d,2d] */
+  const float *mlp2;              /* [d,2d]  */
+  const float *norm1_w, *norm1_b, *norm2_w, *norm2_b; /* [d] */
+} UfoLoftrLayer;
+
+typedef struct {
+  const float *w0, *b0, *w2, *b2, *w4, *b4;
+} UfoMlp3;
+
+typedef struct {
+  UfoLoftrLayer view;    /* density_view_transformer.layers.0, d = 80 */
+  UfoLoftrLayer ray;     /* density_ray_transformer.layers.0,  d = 88 */
+  UfoMlp3 pre_sim;       /* pre_sim_mlp            8 -> 32 -> 32 -> 16 */
+  UfoMlp3 density;       /* DensityMLP            88 -> 32 -> 16 -> 1  */
+  UfoMlp3 radiance;      /* linear_radianceweight_1_softmax 83 -> 16 -> 8 -> 1 */
+  const float* view_token;      /* viewToken.view_token [80]       */
+  const float* depth_freqs;     /* depthcode._freqs  [8]           */
+  const float* depth_phases;    /* depthcode._phases [8]           */
+  float variance;               /* deviation_network.variance      */
+} UfoWeightsDesc;
+
+/* Optional device buffers that receive intermediate tensors of the FINE pass (second sample2rgb
+ * call, 128 samples) and the coarse pass; any pointer may be NULL.  Used by the parity tests at the
+ * reference's sub-boundaries. */
+typedef struct {
+  float* z_coarse;      /* [n,64]        FixedSampler z                 sampler.py:15-50   */
+  float* weight_coarse; /* [n,64]        renderer weights, coarse pass  renderer.py:41     */
+  float* srdf_coarse;   /* [n,64]                                                          */
+  float* z_fine;        /* [n,64]        ImportanceSampler z (sorted)   sampler.py:74-108  */
+  float* sim8;          /* [n,128,8]     query_cond_info feat_info      model.py:218-305   */
+  float* vol24;         /* [n,128,24]    query_depth_from_volume        model.py:350-390   */
+  float* tokens;        /* [n,128,NV,80] view tokens before the view transformer           */
+  float* view_tok0;     /* [n,128,80]    view-transformer output, token 0                  */
+  float* ray_out;       /* [n,128,88]    ray-transformer output                            */
+  float* radiance;      /* [n,128,3]     blended colour per sample                         */
+  float* weight;        /* [n,128]       renderer weights, fine pass                       */
+} UfoDebugTaps;
+
+typedef struct {
+  float* depth;   /* [dev] [n]      ray-distance depth  (infer's depth_2, model.py:478)        */
+  float* depth_z; /* [dev] [n]      depth * cam_ray_d.z (extract_geometry, model.py:818-821)   */
+  float* rgb;     /* [dev] [n,3]                                                               */
+  float* srdf;    /* [dev] [n,128]  may be NULL                                                */
+  float* z;       /* [dev] [n,128]  sorted sample distances; may be NULL                       */
+  float* points;  /* [dev] [n,128,3] may be NULL                                               */
+} UfoRenderOut;
+
+int ufo_abi_version(void);
+const char* ufo_last_error(void);
+
+/* Device properties the host side needs (SM count for sharding heuristics). */
+int ufo_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+
+/* Pack the hot-path weights (replaces nn.Module state of RayTransformer / SingleVarianceNetwork). */
+int ufo_weights_create(const UfoWeightsDesc* desc, UfoWeights** out, void* stream);
+void ufo_weights_destroy(UfoWeights* w);
+
+/* Repack one view set (replaces nothing in the reference - it keeps NCHW tensors; the fused
+ * gathers want channel-last texels).  Synchronous w.r.t. `stream` ordering only. */
+int ufo_scene_create(const UfoSceneDesc* desc, UfoScene** out, void* stream);
+void ufo_scene_destroy(UfoScene* s);
+/* Bytes of device memory owned by the scene (for DESIGN.md's layout accounting). */
+int64_t ufo_scene_device_bytes(const UfoScene* s);
+
+/* UFORecon.infer(extract_geometry=True) for `n_rays` rays (code1/model.py:393-478):
+ * coarse sampling (sampler.py:15-50) -> sample2rgb (model.py:308-348) -> importance sampling
+ * (sampler.py:74-108) -> merge+sort (model.py:466-470) -> sample2rgb on all 128 samples.
+ *   ray_idx   [dev] int64 [n_rays] pixel indices h*W+w, or NULL for the range
+ *             [ray_begin, ray_begin+n_rays)
+ *   u_coarse  [dev] [64, u_stride]  uniforms of FixedSampler's jitter, column i <-> ray i
+ *   u_fine    [dev] [64, u_stride]  uniforms of ImportanceSampler (reference draws [64,RN] and
+ *             transposes, sampler.py:86); u_stride >= n_rays is the row pitch in floats
+ *   mode      UFO_MODE_FP32 | UFO_MODE_TC
+ */
+int ufo_render_rays(const UfoScene* scene, const UfoWeights* weights, const int64_t* ray_idx,
+                    int64_t ray_begin, int32_t n_rays, const float* u_coarse, const float* u_fine,
+                    int64_t u_stride, int32_t mode, const UfoRenderOut* out,
+                    const UfoDebugTaps* taps, void* stream);
+
+/* Same call with HOST buffers: copies uniforms host->device, renders, copies depth_z/rgb back and
+ * synchronises the stream.  u_* are [64,n_rays] pinned or pageable host memory; depth_z [n_rays],
+ * rgb [n_rays,3] host.  Rays are the range [ray_begin, ray_begin+n_rays). */
+int ufo_render_rays_host(const UfoScene* scene, const UfoWeights* weights, int64_t ray_begin,
+                         int32_t n_rays, const float* u_coarse_host, const float* u_fine_host,
+                         int32_t mode, float* depth_z_host, float* rgb_host, void* stream);
+
+/* Number of kernel launches issued by this library since process start (bench.py's gpu_launches). */
+int64_t ufo_launch_count(void);
+
+/* Cost-volume build of one cascade stage for all N reference rotations (replaces the loop of
+ * DepthNet.forward, TransMVSNet.py:76-100, with homo_warping_trans, fmt/module.py:329-367 and
+ * PixelwiseNet, TransMVSNet.py:23-41; the 3-D CNN regulariser stays in PyTorch).
+ *   feats       [dev] [V][N,C,h,w]   V = views per rotation; feats[0] = reference features
+ *   proj        [host] [N,V,2,4,4]   proj_matrices of this stage
+ *   depth_hyp   [dev] [N,D,h,w]
+ *   view_w_in   [dev] [N,V-1,h,w] or NULL (stage 1: computed from pixelwise net)
+ *   pw          [host] folded PixelwiseNet parameters, see UfoPixelwiseNet; ignored if view_w_in
+ *   similarity  [dev] [N,1,D,h,w]  out
+ *   view_w_out  [dev] [N,V-1,h,w]  out (written only when view_w_in == NULL)
+ */
+typedef struct {
+  const float *conv0_w;                              /* [16]  (1->16, 1x1x1, no bias)            */
+  const float *bn0_w, *bn0_b, *bn0_mean, *bn0_var;   /* [16]                                     */
+  const float *conv1_w;                              /* [8,16]                                   */
+  const float *bn1_w, *bn1_b, *bn1_mean, *bn1_var;   /* [8]                                      */
+  const float *conv2_w;                              /* [8]                                      */
+  float conv2_b;
+} UfoPixelwiseNet;
+
+int ufo_costvolume_stage(const float* const* feats, int32_t n_rot, int32_t n_views, int32_t channels,
+                         int32_t h, int32_t w, int32_t n_depth, const float* proj,
+                         const float* depth_hyp, const float* view_w_in, const UfoPixelwiseNet* pw,
+                         float* similarity, float* view_w_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UFORECON_B200_H_ */

@@ -1,0 +1,175 @@
+"""GPU: the CUDA path through the C ABI against the oracle and the committed reference goldens.
+
+Tolerances (north star): fp32 gather / sampler / compositing kernels within 1e-5 relative
+(max |a-b| / max |ref|); each kernel is isolated by feeding the oracle the CUDA path's own upstream
+tensors (taps), so that a tolerance is a statement about ONE kernel.  End to end (fp32 mode) the bar is
+1e-4 on depth / rgb because the importance sampler and the NeuS alpha amplify upstream rounding.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, make_case, rel_err
+from oracle import uforecon_oracle as orc
+from uforecon_b200 import synthetic
+from uforecon_b200._lib import UFO_MODE_FP32, UFO_MODE_TC
+
+pytestmark = pytest.mark.gpu
+
+ALL_TAPS = ("z_coarse", "weight_coarse", "srdf_coarse", "z_fine", "sim8", "vol24", "tokens", "view_tok0", "ray_out",
+            "radiance", "weight")
+
+
+def run_cuda(batch, scene, sd, ray_idx, u_c, u_f, mode, taps=ALL_TAPS):
+    from uforecon_b200.renderer import HotPathWeights, Scene, render_rays
+    w = HotPathWeights(sd)
+    sc = Scene(batch, scene["source_imgs_feat"], scene["feature_volume"], scene["match_feature"])
+    r = render_rays(sc, w, ray_idx, len(ray_idx), u_c, u_f, mode, want=("depth", "depth_z", "rgb", "srdf", "z", "points"),
+                    taps=taps)
+    torch.cuda.synchronize()
+    r = {k: v.cpu() for k, v in r.items()}
+    sc.close()
+    w.close()
+    return r
+
+
+@pytest.fixture(scope="module", params=["nv3", "nv5"])
+def case(request):
+    g = load_golden(f"infer_{request.param}.npz")
+    W, H, seed, dr = [int(x) for x in g["meta"][:4]]
+    views = [int(x) for x in g["meta"][4:]]
+    batch, scene, sd = make_case(views, (W, H))
+    ray_idx = torch.from_numpy(g["ray_idx"])
+    u_c, u_f = synthetic.sampler_uniforms(len(ray_idx), seed=seed)
+    with torch.no_grad():
+        o = orc.infer(batch, scene, sd, ray_idx, u_c, u_f, detail=True)
+    r = run_cuda(batch, scene, sd, ray_idx, u_c, u_f, UFO_MODE_FP32)
+    return dict(g=g, batch=batch, scene=scene, sd=sd, ray_idx=ray_idx, u_c=u_c, u_f=u_f, o=o, r=r, nv=len(views), dr=dr)
+
+
+def test_coarse_sampler(case):
+    assert rel_err(case["r"]["z_coarse"], case["o"]["z_coarse"]) <= 1e-6
+    assert rel_err(case["r"]["z_coarse"], case["g"]["z_coarse"]) <= 1e-6
+
+
+def _pts_from_z(case, z):
+    batch, ray_idx = case["batch"], case["ray_idx"]
+    d = batch["ray_d"][0][:, ray_idx].t()
+    return (batch["ray_o"][0][None, None] + z[:, :, None] * d[:, None, :]).float()
+
+
+def test_gather_kernels_isolated(case):
+    """projection + bilinear/trilinear gathers + similarity prior + volume blend + depth PE at the CUDA path's own z."""
+    batch, scene, sd, r = case["batch"], case["scene"], case["sd"], case["r"]
+    z = r["z"]
+    pts = _pts_from_z(case, z)
+    assert rel_err(r["points"], pts) <= 1e-6
+    with torch.no_grad():
+        o = orc.sample2rgb(batch, scene, sd, pts, z, detail=True)
+    RN = z.shape[0]
+    assert rel_err(r["sim8"], o["sim8"]) <= 1e-5
+    assert rel_err(r["vol24"], o["vol24"]) <= 1e-5
+    tok = o["tokens"].view(RN, 128, case["nv"], 80)
+    # sim16 columns (56:72) go through pre_sim_mlp: same 1e-5 bar
+    assert rel_err(r["tokens"][..., :32], tok[..., :32]) <= 1e-5
+    assert rel_err(r["tokens"][..., 32:56], tok[..., 32:56]) <= 1e-5
+    assert rel_err(r["tokens"][..., 56:72], tok[..., 56:72]) <= 1e-5
+    assert rel_err(r["tokens"][..., 72:], tok[..., 72:]) <= 2e-5   # sin() of arguments up to ~8*pi*|delta|
+
+
+def test_transformer_fp32_isolated(case):
+    batch, scene, sd, r = case["batch"], case["scene"], case["sd"], case["r"]
+    z = r["z"]
+    pts = _pts_from_z(case, z)
+    RN = z.shape[0]
+    with torch.no_grad():
+        o = orc.sample2rgb(batch, scene, sd, pts, z, detail=True)
+    assert rel_err(r["view_tok0"], o["view_out"].view(RN, 128, case["nv"] + 1, 80)[:, :, 0]) <= 2e-5
+    assert rel_err(r["ray_out"], o["ray_out"]) <= 2e-5
+    assert rel_err(r["srdf"], o["srdf"]) <= 2e-5
+    assert rel_err(r["radiance"], o["radiance"]) <= 2e-5
+
+
+def test_compositing_isolated(case):
+    r, sd = case["r"], case["sd"]
+    with torch.no_grad():
+        rgb, depth, opacity, weight = orc.render(r["z"], r["radiance"], r["srdf"], sd["deviation_network.variance"])
+        _, _, _, weight_c = orc.render(r["z_coarse"], torch.zeros(r["z_coarse"].shape + (3,)), r["srdf_coarse"],
+                                       sd["deviation_network.variance"])
+    assert rel_err(r["weight"], weight) <= 1e-5
+    assert rel_err(r["depth"], depth) <= 1e-5
+    assert rel_err(r["rgb"], rgb) <= 1e-5
+    assert rel_err(r["weight_coarse"], weight_c) <= 1e-5
+    cz = case["batch"]["cam_ray_d"][0][2, case["ray_idx"]]
+    assert rel_err(r["depth_z"], r["depth"] * cz) <= 1e-6
+
+
+def test_importance_sampler_isolated(case):
+    r, batch = case["r"], case["batch"]
+    ray_idx = case["ray_idx"]
+    d = batch["ray_d"][0][:, ray_idx].t()
+    o = batch["ray_o"][0][None].expand_as(d)
+    _, z2 = orc.importance_sampler(o, d, r["weight_coarse"], r["z_coarse"], case["u_f"].t())
+    assert rel_err(r["z_fine"], z2) <= 1e-5
+    z_all = torch.sort(torch.cat([r["z_coarse"], r["z_fine"]], 1), dim=1)[0]
+    assert torch.equal(r["z"], z_all)          # merge is exact
+
+
+def test_end_to_end_fp32_vs_oracle_and_golden(case):
+    r, o, g = case["r"], case["o"], case["g"]
+    for ref in (o, g):
+        assert rel_err(r["depth"], ref["depth"]) <= 1e-4
+        assert rel_err(r["rgb"], ref["rgb"]) <= 1e-4
+        assert rel_err(r["z"], ref["z"]) <= 1e-4
+        assert rel_err(r["srdf"], ref["srdf"]) <= 2e-4
+    dr = case["dr"]
+    assert rel_err(r["sim8"][:dr], g["sim8_f"]) <= 1e-4
+    assert rel_err(r["vol24"][:dr], g["vol24_f"]) <= 1e-4
+
+
+def test_chunking_and_ray_range_invariance():
+    """n shards == 1 shard: rays are independent, so any tiling gives identical results."""
+    import os
+    batch, scene, sd = make_case(synthetic.UNFAVORABLE_VIEWS, (96, 64))
+    n = 300
+    u_c, u_f = synthetic.sampler_uniforms(n, seed=5)
+    from uforecon_b200.renderer import HotPathWeights, Scene, render_rays
+    w = HotPathWeights(sd)
+    sc = Scene(batch, scene["source_imgs_feat"], scene["feature_volume"], scene["match_feature"])
+    full = render_rays(sc, w, None, n, u_c, u_f, UFO_MODE_FP32, ray_begin=1000)
+    os.environ["UFO_FP32_CHUNK"] = "64"
+    try:
+        tiled = render_rays(sc, w, None, n, u_c, u_f, UFO_MODE_FP32, ray_begin=1000)
+    finally:
+        del os.environ["UFO_FP32_CHUNK"]
+    idx = torch.arange(1000, 1000 + n)
+    by_idx = render_rays(sc, w, idx, n, u_c, u_f, UFO_MODE_FP32)
+    part = render_rays(sc, w, None, 100, u_c[:, 100:200].contiguous(), u_f[:, 100:200].contiguous(), UFO_MODE_FP32, ray_begin=1100)
+    torch.cuda.synchronize()
+    for k in ("depth", "rgb", "depth_z"):
+        assert torch.equal(full[k], tiled[k]), k
+        assert torch.equal(full[k], by_idx[k]), k
+        assert torch.equal(full[k][100:200], part[k]), k
+    sc.close()
+    w.close()
+
+
+def test_api_errors():
+    from uforecon_b200 import _lib
+    from uforecon_b200.renderer import HotPathWeights, Scene, render_rays
+    batch, scene, sd = make_case(synthetic.UNFAVORABLE_VIEWS, (96, 64))
+    w = HotPathWeights(sd)
+    sc = Scene(batch, scene["source_imgs_feat"], scene["feature_volume"], scene["match_feature"])
+    u_c, u_f = synthetic.sampler_uniforms(8, seed=5)
+    with pytest.raises(_lib.UfoError):
+        render_rays(sc, w, None, 8, u_c, u_f, UFO_MODE_FP32, ray_begin=96 * 64 - 4)   # range outside grid
+    with pytest.raises(_lib.UfoError):
+        render_rays(sc, w, None, 8, u_c, u_f, 7)                                        # unknown mode
+    bad = dict(sd)
+    del bad["ray_transformer.viewToken.view_token"]
+    with pytest.raises(KeyError):
+        HotPathWeights(bad)
+    r = render_rays(sc, w, None, 0, u_c, u_f, UFO_MODE_FP32)                            # empty ray set is a no-op
+    assert r["depth"].numel() == 0
+    sc.close()
+    w.close()

@@ -1,0 +1,71 @@
+"""Host-side mirror of the cost-volume build inside ``DepthNet.forward`` (kernel 1).
+
+``similarity_volume`` takes what ``DepthNet.forward`` takes (code1/encoder_utils/fmt/TransMVSNet.py:49)
+and returns the tensor it hands to ``cost_regularization`` (TransMVSNet.py:100-103) plus the view
+weights of stage 1 (TransMVSNet.py:118-119).  The 3-D CNN regulariser stays in PyTorch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from .renderer import _dev_f32, _host_f32, _stream_ptr
+
+PW = "transmvsnet.DepthNet.pixel_wise_net."
+
+
+def _pixelwise_desc(state_dict: Dict[str, torch.Tensor], keep: list) -> _lib.UfoPixelwiseNet:
+    def p(name):
+        t = _host_f32(state_dict[PW + name]).reshape(-1).contiguous()
+        keep.append(t)
+        return t.data_ptr()
+    d = _lib.UfoPixelwiseNet()
+    d.conv0_w = p("conv0.conv.weight")
+    d.bn0_w, d.bn0_b, d.bn0_mean, d.bn0_var = p("conv0.bn.weight"), p("conv0.bn.bias"), p("conv0.bn.running_mean"), p("conv0.bn.running_var")
+    d.conv1_w = p("conv1.conv.weight")
+    d.bn1_w, d.bn1_b, d.bn1_mean, d.bn1_var = p("conv1.bn.weight"), p("conv1.bn.bias"), p("conv1.bn.running_mean"), p("conv1.bn.running_var")
+    d.conv2_w = p("conv2.weight")
+    d.conv2_b = float(state_dict[PW + "conv2.bias"].reshape(-1)[0])
+    return d
+
+
+def similarity_volume(features: Sequence[torch.Tensor], proj_matrices: torch.Tensor, depth_values: torch.Tensor,
+                      state_dict: Optional[Dict[str, torch.Tensor]] = None, view_weights: Optional[torch.Tensor] = None,
+                      device=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """features: V tensors [N,C,h,w] (slot 0 = reference); proj_matrices [N,V,2,4,4];
+    depth_values [N,D,h,w]; view_weights [N,V-1,h,w] or None (stage 1).
+    Returns (similarity [N,1,D,h,w], view_weights [N,V-1,h,w])."""
+    lib = _lib.load()
+    dev = torch.device(device if device is not None else "cuda")
+    V = len(features)
+    N, Cc, h, w = features[0].shape
+    D = depth_values.shape[1]
+    if tuple(proj_matrices.shape) != (N, V, 2, 4, 4):
+        raise ValueError(f"proj_matrices shape {tuple(proj_matrices.shape)} != {(N, V, 2, 4, 4)}")
+    if tuple(depth_values.shape) != (N, D, h, w):
+        raise ValueError("depth_values must be [N,D,h,w]")
+    keep: list = []
+    fe = [_dev_f32(f, dev) for f in features]
+    ptrs = (C.c_void_p * V)(*[f.data_ptr() for f in fe])
+    proj = _host_f32(proj_matrices)
+    hyp = _dev_f32(depth_values, dev)
+    sim = torch.empty(N, 1, D, h, w, dtype=torch.float32, device=dev)
+    if view_weights is None:
+        if state_dict is None:
+            raise ValueError("stage 1 needs the pixel-wise net weights (state_dict)")
+        pw = _pixelwise_desc(state_dict, keep)
+        vw_out = torch.empty(N, V - 1, h, w, dtype=torch.float32, device=dev)
+        vw_in_ptr, pw_ref = None, C.byref(pw)
+    else:
+        vw_in = _dev_f32(view_weights, dev)
+        vw_out = vw_in
+        vw_in_ptr, pw_ref = vw_in.data_ptr(), None
+    with torch.cuda.device(dev):
+        _lib.check(lib.ufo_costvolume_stage(ptrs, N, V, Cc, h, w, D, proj.data_ptr(), hyp.data_ptr(), vw_in_ptr, pw_ref,
+                                            sim.data_ptr(), vw_out.data_ptr() if view_weights is None else None,
+                                            _stream_ptr(dev)))
+        torch.cuda.current_stream(dev).synchronize()
+    return sim, vw_out

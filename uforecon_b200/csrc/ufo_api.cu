@@ -1,0 +1,663 @@
+// C-ABI entry points of libuforecon_b200.so (declared in include/uforecon_b200.h).
+#include <cmath>
+#include <cstdlib>
+#include <mutex>
+#include <vector>
+
+#include "ufo_common.cuh"
+#include "ufo_costvol.cuh"
+#include "ufo_gather.cuh"
+#include "ufo_repack.cuh"
+#include "ufo_sampler_render.cuh"
+#include "ufo_xfmr_fp32.cuh"
+#include "ufo_xfmr_tc.cuh"
+
+namespace ufo {
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+}  // namespace ufo
+
+using namespace ufo;
+
+// ------------------------------------------------------------------------------------------------
+// handles
+// ------------------------------------------------------------------------------------------------
+struct LoftrDev {
+  const float *qkv, *merge, *mlp0, *mlp2, *n1w, *n1b, *n2w, *n2b;
+};
+
+struct UfoWeights {
+  int device = -1;
+  float* blob = nullptr;  // all fp32 tensors, one allocation
+  size_t blob_floats = 0;
+  LoftrDev view{}, ray{};
+  Mlp3Dev pre_sim{}, density{}, radiance{};
+  const float *view_token = nullptr, *freqs = nullptr, *phases = nullptr, *pe_table = nullptr;  // pe_table [128][8]
+  float inv_s = 1.f;
+  TcWeights tc;  // bf16 operand images for the tensor-core path
+};
+
+struct Workspace {
+  float* base = nullptr;
+  size_t floats = 0;
+  int cap_rays = 0, nv = 0;
+  float *rayinfo, *z_c, *z_all, *z_fine, *XV, *QKV, *MSG, *MRG, *H1, *Y2, *VOUT, *XR, *ROUT, *sim8, *radiance, *srdf,
+      *weight, *pts;
+  float4 *rgbm, *dirs;
+};
+
+struct UfoScene {
+  int device = -1;
+  SceneDev d{};
+  std::vector<void*> owned;
+  int64_t bytes = 0;
+  mutable Workspace ws;
+  mutable float* u_dev = nullptr;      // staging for ufo_render_rays_host
+  mutable float* out_dev = nullptr;
+  mutable size_t u_cap = 0;
+  mutable std::mutex mu;
+};
+
+static int check_device() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(UFO_ENODEVICE, "no CUDA device visible: libuforecon_b200 has no CPU fallback");
+  }
+  return UFO_OK;
+}
+
+extern "C" int ufo_abi_version(void) { return UFO_ABI_VERSION; }
+extern "C" const char* ufo_last_error(void) { return g_err; }
+extern "C" int64_t ufo_launch_count(void) { return (int64_t)g_launches.load(); }
+
+extern "C" int ufo_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
+  if (int e = check_device()) return e;
+  int dev = 0;
+  UFO_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  UFO_CUDA(cudaGetDeviceProperties(&p, dev));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  return UFO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weights
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct BlobBuilder {
+  std::vector<float> host;
+  size_t add(const float* p, size_t n) {
+    size_t off = (host.size() + 3) & ~size_t(3);  // 16-byte aligned tensors
+    host.resize(off + n);
+    memcpy(host.data() + off, p, n * sizeof(float));
+    return off;
+  }
+};
+}  // namespace
+
+extern "C" int ufo_weights_create(const UfoWeightsDesc* d, UfoWeights** out, void* stream_) {
+  if (!d || !out) return fail(UFO_EINVAL, "ufo_weights_create: null argument");
+  if (int e = check_device()) return e;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const UfoLoftrLayer* ll[2] = {&d->view, &d->ray};
+  for (int i = 0; i < 2; ++i) {
+    const UfoLoftrLayer* l = ll[i];
+    if (!l->q || !l->k || !l->v || !l->merge || !l->mlp0 || !l->mlp2 || !l->norm1_w || !l->norm1_b || !l->norm2_w ||
+        !l->norm2_b)
+      return fail(UFO_EINVAL, "ufo_weights_create: missing transformer tensor");
+  }
+  const UfoMlp3* mm[3] = {&d->pre_sim, &d->density, &d->radiance};
+  for (int i = 0; i < 3; ++i)
+    if (!mm[i]->w0 || !mm[i]->b0 || !mm[i]->w2 || !mm[i]->b2 || !mm[i]->w4 || !mm[i]->b4)
+      return fail(UFO_EINVAL, "ufo_weights_create: missing MLP tensor");
+  if (!d->view_token || !d->depth_freqs || !d->depth_phases) return fail(UFO_EINVAL, "ufo_weights_create: missing tensor");
+
+  UfoWeights* w = new UfoWeights();
+  UFO_CUDA(cudaGetDevice(&w->device));
+  BlobBuilder b;
+  size_t off[64];
+  int k = 0;
+  const int dims[2] = {kDView, kDRay};
+  for (int i = 0; i < 2; ++i) {
+    const int dm = dims[i];
+    const UfoLoftrLayer* l = ll[i];
+    std::vector<float> qkv((size_t)3 * dm * dm);
+    memcpy(qkv.data(), l->q, sizeof(float) * dm * dm);
+    memcpy(qkv.data() + (size_t)dm * dm, l->k, sizeof(float) * dm * dm);
+    memcpy(qkv.data() + (size_t)2 * dm * dm, l->v, sizeof(float) * dm * dm);
+    off[k++] = b.add(qkv.data(), qkv.size());
+    off[k++] = b.add(l->merge, (size_t)dm * dm);
+    off[k++] = b.add(l->mlp0, (size_t)4 * dm * dm);
+    off[k++] = b.add(l->mlp2, (size_t)2 * dm * dm);
+    off[k++] = b.add(l->norm1_w, dm);
+    off[k++] = b.add(l->norm1_b, dm);
+    off[k++] = b.add(l->norm2_w, dm);
+    off[k++] = b.add(l->norm2_b, dm);
+  }
+  const int mdim[3][4] = {{8, 32, 32, 16}, {kDRay, 32, 16, 1}, {kDView + 3, 16, 8, 1}};
+  for (int i = 0; i < 3; ++i) {
+    off[k++] = b.add(mm[i]->w0, (size_t)mdim[i][0] * mdim[i][1]);
+    off[k++] = b.add(mm[i]->b0, mdim[i][1]);
+    off[k++] = b.add(mm[i]->w2, (size_t)mdim[i][1] * mdim[i][2]);
+    off[k++] = b.add(mm[i]->b2, mdim[i][2]);
+    off[k++] = b.add(mm[i]->w4, (size_t)mdim[i][2] * mdim[i][3]);
+    off[k++] = b.add(mm[i]->b4, mdim[i][3]);
+  }
+  off[k++] = b.add(d->view_token, kDView);
+  off[k++] = b.add(d->depth_freqs, 8);
+  off[k++] = b.add(d->depth_phases, 8);
+  // sample-order sinusoid table (ray_transformer.py:165-173), float64 then cast like the reference
+  std::vector<float> pe((size_t)kNS * 8);
+  for (int i = 0; i < kNS; ++i)
+    for (int j = 0; j < 8; ++j) {
+      const double ang = (double)i / std::pow(10000.0, 2.0 * (double)(j / 2) / 8.0);
+      pe[(size_t)i * 8 + j] = (float)((j % 2 == 0) ? std::sin(ang) : std::cos(ang));
+    }
+  off[k++] = b.add(pe.data(), pe.size());
+
+  w->blob_floats = b.host.size();
+  UFO_CUDA(cudaMalloc(&w->blob, w->blob_floats * sizeof(float)));
+  UFO_CUDA(cudaMemcpyAsync(w->blob, b.host.data(), w->blob_floats * sizeof(float), cudaMemcpyHostToDevice, stream));
+  UFO_CUDA(cudaStreamSynchronize(stream));
+  k = 0;
+  LoftrDev* ld[2] = {&w->view, &w->ray};
+  for (int i = 0; i < 2; ++i) {
+    ld[i]->qkv = w->blob + off[k++];
+    ld[i]->merge = w->blob + off[k++];
+    ld[i]->mlp0 = w->blob + off[k++];
+    ld[i]->mlp2 = w->blob + off[k++];
+    ld[i]->n1w = w->blob + off[k++];
+    ld[i]->n1b = w->blob + off[k++];
+    ld[i]->n2w = w->blob + off[k++];
+    ld[i]->n2b = w->blob + off[k++];
+  }
+  Mlp3Dev* md[3] = {&w->pre_sim, &w->density, &w->radiance};
+  for (int i = 0; i < 3; ++i) {
+    md[i]->w0 = w->blob + off[k++];
+    md[i]->b0 = w->blob + off[k++];
+    md[i]->w2 = w->blob + off[k++];
+    md[i]->b2 = w->blob + off[k++];
+    md[i]->w4 = w->blob + off[k++];
+    md[i]->b4 = w->blob + off[k++];
+  }
+  w->view_token = w->blob + off[k++];
+  w->freqs = w->blob + off[k++];
+  w->phases = w->blob + off[k++];
+  w->pe_table = w->blob + off[k++];
+  // SingleVarianceNetwork: exp(10*variance) clipped to [1e-6, 1e6] (single_variance_network.py:11, renderer.py:25)
+  w->inv_s = fminf(fmaxf(expf(d->variance * 10.0f), 1e-6f), 1e6f);
+  if (int e = tc_weights_create(d, &w->tc, stream)) {
+    cudaFree(w->blob);
+    delete w;
+    return e;
+  }
+  *out = w;
+  return UFO_OK;
+}
+
+extern "C" void ufo_weights_destroy(UfoWeights* w) {
+  if (!w) return;
+  tc_weights_destroy(&w->tc);
+  cudaFree(w->blob);
+  delete w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// scene
+// ------------------------------------------------------------------------------------------------
+template <int C>
+static int repack_cl(const float* in, float* out, long long S, int N, cudaStream_t st) {
+  dim3 grid(cdiv(S, 32), N);
+  k_nchw_to_nhwc<C><<<grid, 256, 0, st>>>(in, out, S);
+  UFO_LAUNCH_CHECK();
+  return UFO_OK;
+}
+
+extern "C" int ufo_scene_create(const UfoSceneDesc* d, UfoScene** out, void* stream_) {
+  if (!d || !out) return fail(UFO_EINVAL, "ufo_scene_create: null argument");
+  if (int e = check_device()) return e;
+  if (d->n_views < 2 || d->n_views > UFO_MAX_VIEWS)
+    return fail(UFO_EINVAL, "ufo_scene_create: n_views=%d outside [2,%d]", d->n_views, UFO_MAX_VIEWS);
+  if (d->img_h <= 0 || d->img_w <= 0 || d->feat_h <= 0 || d->feat_w <= 0) return fail(UFO_EINVAL, "ufo_scene_create: bad size");
+  if (!d->source_imgs || !d->img_feats || !d->depth_info || !d->match_feats || !d->source_poses || !d->source_poses_inv ||
+      !d->ref_pose_inv || !d->w2cs || !d->near_fars || !d->ray_o || !d->ray_d || !d->cam_ray_d)
+    return fail(UFO_EINVAL, "ufo_scene_create: null tensor pointer");
+  for (int s = 0; s < 3; ++s)
+    if (!d->vol_feat[s] || !d->vol_weight[s] || d->vol_d[s] <= 0 || d->vol_h[s] <= 0 || d->vol_w[s] <= 0)
+      return fail(UFO_EINVAL, "ufo_scene_create: bad volume %d", s);
+  cudaStream_t st = (cudaStream_t)stream_;
+  UfoScene* sc = new UfoScene();
+  UFO_CUDA(cudaGetDevice(&sc->device));
+  SceneDev& D = sc->d;
+  const int nv = d->n_views;
+  D.nv = nv; D.H = d->img_h; D.W = d->img_w; D.h = d->feat_h; D.w = d->feat_w;
+  auto dalloc = [&](size_t bytes, void** p) -> int {
+    UFO_CUDA(cudaMalloc(p, bytes));
+    sc->owned.push_back(*p);
+    sc->bytes += (int64_t)bytes;
+    return UFO_OK;
+  };
+  int e;
+  const long long hw = (long long)D.h * D.w, HW = (long long)D.H * D.W;
+  float* feat_cl; float4* rgbd; float* match_cl;
+  if ((e = dalloc(sizeof(float) * nv * hw * kFeatC, (void**)&feat_cl))) { ufo_scene_destroy(sc); return e; }
+  if ((e = dalloc(sizeof(float4) * nv * HW, (void**)&rgbd))) { ufo_scene_destroy(sc); return e; }
+  if ((e = dalloc(sizeof(float) * nv * (nv - 1) * hw * kFeatC, (void**)&match_cl))) { ufo_scene_destroy(sc); return e; }
+  if ((e = repack_cl<kFeatC>(d->img_feats, feat_cl, hw, nv, st))) { ufo_scene_destroy(sc); return e; }
+  if ((e = repack_cl<kFeatC>(d->match_feats, match_cl, hw, nv * (nv - 1), st))) { ufo_scene_destroy(sc); return e; }
+  k_pack_rgbd<<<cdiv(HW * nv, 256), 256, 0, st>>>(d->source_imgs, d->depth_info, rgbd, HW, nv);
+  UFO_LAUNCH_CHECK();
+  D.feat_cl = feat_cl; D.rgbd_cl = rgbd; D.match_cl = match_cl;
+  for (int s = 0; s < 3; ++s) {
+    D.vd[s] = d->vol_d[s]; D.vh[s] = d->vol_h[s]; D.vw[s] = d->vol_w[s];
+    const long long vox = (long long)D.vd[s] * D.vh[s] * D.vw[s];
+    float* vf;
+    if ((e = dalloc(sizeof(float) * nv * vox * kVolC, (void**)&vf))) { ufo_scene_destroy(sc); return e; }
+    if ((e = repack_cl<kVolC>(d->vol_feat[s], vf, vox, nv, st))) { ufo_scene_destroy(sc); return e; }
+    D.vol_feat_cl[s] = vf;
+    float* vw;  // single channel: layout already [NV][D][h][w]; copied so the scene owns its inputs
+    if ((e = dalloc(sizeof(float) * nv * vox, (void**)&vw))) { ufo_scene_destroy(sc); return e; }
+    UFO_CUDA(cudaMemcpyAsync(vw, d->vol_weight[s], sizeof(float) * nv * vox, cudaMemcpyDeviceToDevice, st));
+    D.vol_w[s] = vw;
+  }
+  float *rd, *crd;
+  if ((e = dalloc(sizeof(float) * 3 * HW, (void**)&rd))) { ufo_scene_destroy(sc); return e; }
+  if ((e = dalloc(sizeof(float) * 3 * HW, (void**)&crd))) { ufo_scene_destroy(sc); return e; }
+  UFO_CUDA(cudaMemcpyAsync(rd, d->ray_d, sizeof(float) * 3 * HW, cudaMemcpyDeviceToDevice, st));
+  UFO_CUDA(cudaMemcpyAsync(crd, d->cam_ray_d, sizeof(float) * 3 * HW, cudaMemcpyDeviceToDevice, st));
+  D.ray_d = rd; D.cam_ray_d = crd;
+  for (int v = 0; v < nv; ++v) {
+    memcpy(D.P[v], d->source_poses + 16 * v, sizeof(float) * 12);
+    memcpy(D.w2c_z[v], d->w2cs + 16 * v + 8, sizeof(float) * 4);
+    for (int i = 0; i < 3; ++i) D.cam_o[v][i] = d->source_poses_inv[16 * v + 4 * i + 3];
+  }
+  for (int i = 0; i < 3; ++i) {
+    D.ref_o[i] = d->ref_pose_inv[4 * i + 3];
+    D.ray_o[i] = d->ray_o[i];
+  }
+  D.near0 = d->near_fars[0];
+  D.far0 = d->near_fars[1];
+  *out = sc;
+  return UFO_OK;
+}
+
+extern "C" void ufo_scene_destroy(UfoScene* s) {
+  if (!s) return;
+  for (void* p : s->owned) cudaFree(p);
+  cudaFree(s->ws.base);
+  cudaFree(s->u_dev);
+  cudaFree(s->out_dev);
+  tc_scene_release(s->device);
+  delete s;
+}
+
+extern "C" int64_t ufo_scene_device_bytes(const UfoScene* s) { return s ? s->bytes : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// exact fp32 pipeline
+// ------------------------------------------------------------------------------------------------
+static int fp32_chunk_rays() {
+  const char* e = getenv("UFO_FP32_CHUNK");
+  int v = e ? atoi(e) : 2048;
+  return v < 32 ? 32 : v;
+}
+
+static int ws_ensure(const UfoScene* sc, int rays) {
+  Workspace& w = sc->ws;
+  const int nv = sc->d.nv, L = nv + 1;
+  if (w.base && w.cap_rays >= rays && w.nv == nv) return UFO_OK;
+  if (w.base) { cudaFree(w.base); w.base = nullptr; }
+  const size_t P = (size_t)rays * kNS;
+  auto mx = [](size_t a, size_t b) { return a > b ? a : b; };
+  struct Item { float** p; size_t n; };
+  float *rgbm_f, *dirs_f;
+  Item items[] = {
+      {&w.rayinfo, (size_t)rays * 8}, {&w.z_c, (size_t)rays * kNC}, {&w.z_all, P}, {&w.z_fine, (size_t)rays * kNC},
+      {&w.XV, P * L * 160}, {&w.QKV, mx(P * L * 240, P * 264)}, {&w.MSG, mx(P * L * 80, P * 88)},
+      {&w.MRG, mx(P * L * 80, P * 88)}, {&w.H1, mx(P * L * 160, P * 176)}, {&w.Y2, mx(P * L * 80, P * 88)},
+      {&w.VOUT, P * L * 80}, {&w.XR, P * 176}, {&w.ROUT, P * 88}, {&w.sim8, P * 8}, {&rgbm_f, P * nv * 4},
+      {&dirs_f, P * nv * 4}, {&w.radiance, P * 4}, {&w.srdf, P}, {&w.weight, P}, {&w.pts, P * 3}};
+  size_t total = 0;
+  for (auto& it : items) total += (it.n + 63) & ~size_t(63);
+  UFO_CUDA(cudaMalloc(&w.base, total * sizeof(float)));
+  size_t off = 0;
+  for (auto& it : items) { *it.p = w.base + off; off += (it.n + 63) & ~size_t(63); }
+  w.rgbm = reinterpret_cast<float4*>(rgbm_f);
+  w.dirs = reinterpret_cast<float4*>(dirs_f);
+  w.floats = total; w.cap_rays = rays; w.nv = nv;
+  return UFO_OK;
+}
+
+template <int K, int N, bool R>
+static int launch_linear(const float* X, int ldx, const float* W, float* Y, int ldy, long long M, int sms, cudaStream_t st) {
+  const size_t smem = sizeof(float) * ((size_t)K * N + 64 * K);
+  static bool attr_set = false;
+  if (!attr_set) {
+    UFO_CUDA(cudaFuncSetAttribute(k_linear<K, N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const long long tiles = (M + 63) / 64;
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  k_linear<K, N, R><<<grid, 256, smem, st>>>(X, ldx, W, Y, ldy, M);
+  UFO_LAUNCH_CHECK();
+  return UFO_OK;
+}
+
+template <int NV>
+static int launch_gather(const UfoScene* sc, const UfoWeights* w, int R, int SN, const float* z, float* pts, cudaStream_t st) {
+  const Workspace& ws = sc->ws;
+  const long long P = (long long)R * SN;
+  k_gather<NV><<<cdiv(P, 32), 256, 0, st>>>(sc->d, ws.rayinfo, z, R, SN, w->freqs, w->phases, ws.XV, ws.sim8, ws.rgbm,
+                                           ws.dirs, pts);
+  UFO_LAUNCH_CHECK();
+  return UFO_OK;
+}
+
+static int dispatch_gather(const UfoScene* sc, const UfoWeights* w, int R, int SN, const float* z, float* pts, cudaStream_t st) {
+  switch (sc->d.nv) {
+    case 2: return launch_gather<2>(sc, w, R, SN, z, pts, st);
+    case 3: return launch_gather<3>(sc, w, R, SN, z, pts, st);
+    case 4: return launch_gather<4>(sc, w, R, SN, z, pts, st);
+    case 5: return launch_gather<5>(sc, w, R, SN, z, pts, st);
+    case 6: return launch_gather<6>(sc, w, R, SN, z, pts, st);
+    case 7: return launch_gather<7>(sc, w, R, SN, z, pts, st);
+    case 8: return launch_gather<8>(sc, w, R, SN, z, pts, st);
+    case 9: return launch_gather<9>(sc, w, R, SN, z, pts, st);
+    case 10: return launch_gather<10>(sc, w, R, SN, z, pts, st);
+  }
+  return fail(UFO_EINVAL, "unsupported n_views");
+}
+
+// One sample2rgb pass (code1/model.py:308-348) over R rays x SN samples, fp32 CUDA-core arithmetic.
+static int pass_fp32(const UfoScene* sc, const UfoWeights* w, int R, int SN, const float* z, int sms, float* pts,
+                     cudaStream_t st) {
+  const Workspace& ws = sc->ws;
+  const int nv = sc->d.nv, L = nv + 1;
+  const long long P = (long long)R * SN, MV = P * L;
+  int e;
+  if ((e = dispatch_gather(sc, w, R, SN, z, pts, st))) return e;
+  k_presim<<<cdiv(P, 128), 128, 0, st>>>(ws.sim8, w->pre_sim, w->view_token, L, P, ws.XV);
+  UFO_LAUNCH_CHECK();
+  // ---- view transformer (tokens = views of one sample point)
+  if ((e = launch_linear<80, 240, false>(ws.XV, 160, w->view.qkv, ws.QKV, 240, MV, sms, st))) return e;
+  k_linattn<10><<<cdiv(P * kHeads, 128), 128, 0, st>>>(ws.QKV, ws.MSG, P, L);
+  UFO_LAUNCH_CHECK();
+  if ((e = launch_linear<80, 80, false>(ws.MSG, 80, w->view.merge, ws.MRG, 80, MV, sms, st))) return e;
+  k_layernorm<80><<<cdiv(MV, 8), 256, 0, st>>>(ws.MRG, 80, w->view.n1w, w->view.n1b, nullptr, 0, ws.XV + 80, 160, MV);
+  UFO_LAUNCH_CHECK();
+  if ((e = launch_linear<160, 160, true>(ws.XV, 160, w->view.mlp0, ws.H1, 160, MV, sms, st))) return e;
+  if ((e = launch_linear<160, 80, false>(ws.H1, 160, w->view.mlp2, ws.Y2, 80, MV, sms, st))) return e;
+  k_layernorm<80><<<cdiv(MV, 8), 256, 0, st>>>(ws.Y2, 80, w->view.n2w, w->view.n2b, ws.XV, 160, ws.VOUT, 80, MV);
+  UFO_LAUNCH_CHECK();
+  // ---- ray transformer (tokens = samples of one ray)
+  k_ray_tokens<<<cdiv(P * kDRay, 256), 256, 0, st>>>(ws.VOUT, L, SN, P, w->pe_table, ws.XR);
+  UFO_LAUNCH_CHECK();
+  if ((e = launch_linear<88, 264, false>(ws.XR, 176, w->ray.qkv, ws.QKV, 264, P, sms, st))) return e;
+  k_linattn<11><<<cdiv((long long)R * kHeads, 128), 128, 0, st>>>(ws.QKV, ws.MSG, R, SN);
+  UFO_LAUNCH_CHECK();
+  if ((e = launch_linear<88, 88, false>(ws.MSG, 88, w->ray.merge, ws.MRG, 88, P, sms, st))) return e;
+  k_layernorm<88><<<cdiv(P, 8), 256, 0, st>>>(ws.MRG, 88, w->ray.n1w, w->ray.n1b, nullptr, 0, ws.XR + 88, 176, P);
+  UFO_LAUNCH_CHECK();
+  if ((e = launch_linear<176, 176, true>(ws.XR, 176, w->ray.mlp0, ws.H1, 176, P, sms, st))) return e;
+  if ((e = launch_linear<176, 88, false>(ws.H1, 176, w->ray.mlp2, ws.Y2, 88, P, sms, st))) return e;
+  k_layernorm<88><<<cdiv(P, 8), 256, 0, st>>>(ws.Y2, 88, w->ray.n2w, w->ray.n2b, ws.XR, 176, ws.ROUT, 88, P);
+  UFO_LAUNCH_CHECK();
+  // ---- heads
+  k_density<<<cdiv(P, 128), 128, 0, st>>>(ws.ROUT, w->density, P, ws.srdf);
+  UFO_LAUNCH_CHECK();
+  k_radiance<<<cdiv(P, 128), 128, 0, st>>>(ws.VOUT, ws.dirs, ws.rgbm, w->radiance, nv, P, reinterpret_cast<float4*>(ws.radiance));
+  UFO_LAUNCH_CHECK();
+  return UFO_OK;
+}
+
+__global__ void k_copy_strided(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd, int cols, long long rows) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rows * cols) return;
+  const long long r = t / cols;
+  const int c = (int)(t % cols);
+  dst[r * ldd + c] = src[r * lds + c];
+}
+
+static int copy_rows(const float* src, int lds, float* dst, int ldd, int cols, long long rows, cudaStream_t st) {
+  k_copy_strided<<<cdiv(rows * cols, 256), 256, 0, st>>>(src, lds, dst, ldd, cols, rows);
+  UFO_LAUNCH_CHECK();
+  return UFO_OK;
+}
+
+static int render_chunk_fp32(const UfoScene* sc, const UfoWeights* w, const int64_t* ray_idx, int64_t ray_begin, int R,
+                             const float* u_c, const float* u_f, int64_t u_stride, int64_t off, const UfoRenderOut* out,
+                             const UfoDebugTaps* taps, int sms, cudaStream_t st) {
+  const Workspace& ws = sc->ws;
+  const int nv = sc->d.nv, L = nv + 1;
+  int e;
+  k_ray_setup<<<cdiv(R, 256), 256, 0, st>>>(sc->d, (const long long*)(ray_idx ? ray_idx + off : nullptr), ray_begin + off, R, ws.rayinfo);
+  UFO_LAUNCH_CHECK();
+  k_coarse_z<<<cdiv((long long)R * kNC, 256), 256, 0, st>>>(ws.rayinfo, u_c + off, u_stride, R, ws.z_c);
+  UFO_LAUNCH_CHECK();
+  if ((e = pass_fp32(sc, w, R, kNC, ws.z_c, sms, nullptr, st))) return e;
+  k_render<kNC><<<cdiv(R, 8), 256, 0, st>>>(ws.z_c, ws.srdf, reinterpret_cast<const float4*>(ws.radiance), w->inv_s, R, ws.weight,
+                                          nullptr, nullptr, nullptr, ws.rayinfo);
+  UFO_LAUNCH_CHECK();
+  if (taps) {
+    if (taps->z_coarse) UFO_CUDA(cudaMemcpyAsync(taps->z_coarse + off * kNC, ws.z_c, sizeof(float) * R * kNC, cudaMemcpyDeviceToDevice, st));
+    if (taps->weight_coarse) UFO_CUDA(cudaMemcpyAsync(taps->weight_coarse + off * kNC, ws.weight, sizeof(float) * R * kNC, cudaMemcpyDeviceToDevice, st));
+    if (taps->srdf_coarse) UFO_CUDA(cudaMemcpyAsync(taps->srdf_coarse + off * kNC, ws.srdf, sizeof(float) * R * kNC, cudaMemcpyDeviceToDevice, st));
+  }
+  k_importance<<<cdiv(R, 8), 256, 0, st>>>(ws.weight, ws.z_c, u_f + off, u_stride, R, ws.z_fine, ws.z_all);
+  UFO_LAUNCH_CHECK();
+  float* pts = out->points ? out->points + off * kNS * 3 : nullptr;
+  if ((e = pass_fp32(sc, w, R, kNS, ws.z_all, sms, pts, st))) return e;
+  k_render<kNS><<<cdiv(R, 8), 256, 0, st>>>(ws.z_all, ws.srdf, reinterpret_cast<const float4*>(ws.radiance), w->inv_s, R, ws.weight,
+                                          out->depth ? out->depth + off : nullptr, out->rgb ? out->rgb + off * 3 : nullptr,
+                                          out->depth_z ? out->depth_z + off : nullptr, ws.rayinfo);
+  UFO_LAUNCH_CHECK();
+  const long long P = (long long)R * kNS;
+  if (out->srdf) UFO_CUDA(cudaMemcpyAsync(out->srdf + off * kNS, ws.srdf, sizeof(float) * P, cudaMemcpyDeviceToDevice, st));
+  if (out->z) UFO_CUDA(cudaMemcpyAsync(out->z + off * kNS, ws.z_all, sizeof(float) * P, cudaMemcpyDeviceToDevice, st));
+  if (taps) {
+    const long long po = off * kNS;
+    if (taps->z_fine) UFO_CUDA(cudaMemcpyAsync(taps->z_fine + off * kNC, ws.z_fine, sizeof(float) * R * kNC, cudaMemcpyDeviceToDevice, st));
+    if (taps->sim8) UFO_CUDA(cudaMemcpyAsync(taps->sim8 + po * 8, ws.sim8, sizeof(float) * P * 8, cudaMemcpyDeviceToDevice, st));
+    if (taps->vol24 && (e = copy_rows(ws.XV + 160 + 32, L * 160, taps->vol24 + po * 24, 24, 24, P, st))) return e;
+    if (taps->tokens)
+      for (int n = 0; n < nv; ++n)
+        if ((e = copy_rows(ws.XV + (size_t)(n + 1) * 160, L * 160, taps->tokens + po * nv * 80 + (size_t)n * 80, nv * 80, 80, P, st))) return e;
+    if (taps->view_tok0 && (e = copy_rows(ws.VOUT, L * 80, taps->view_tok0 + po * 80, 80, 80, P, st))) return e;
+    if (taps->ray_out) UFO_CUDA(cudaMemcpyAsync(taps->ray_out + po * 88, ws.ROUT, sizeof(float) * P * 88, cudaMemcpyDeviceToDevice, st));
+    if (taps->radiance && (e = copy_rows(ws.radiance, 4, taps->radiance + po * 3, 3, 3, P, st))) return e;
+    if (taps->weight) UFO_CUDA(cudaMemcpyAsync(taps->weight + po, ws.weight, sizeof(float) * P, cudaMemcpyDeviceToDevice, st));
+  }
+  return UFO_OK;
+}
+
+extern "C" int ufo_render_rays(const UfoScene* sc, const UfoWeights* w, const int64_t* ray_idx, int64_t ray_begin,
+                               int32_t n_rays, const float* u_coarse, const float* u_fine, int64_t u_stride, int32_t mode,
+                               const UfoRenderOut* out, const UfoDebugTaps* taps, void* stream_) {
+  if (!sc || !w || !out || !u_coarse || !u_fine) return fail(UFO_EINVAL, "ufo_render_rays: null argument");
+  if (n_rays < 0 || u_stride < n_rays) return fail(UFO_EINVAL, "ufo_render_rays: bad n_rays/u_stride");
+  if (mode != UFO_MODE_FP32 && mode != UFO_MODE_TC) return fail(UFO_EINVAL, "ufo_render_rays: unknown mode %d", mode);
+  if (!ray_idx && (ray_begin < 0 || ray_begin + n_rays > (int64_t)sc->d.H * sc->d.W))
+    return fail(UFO_EINVAL, "ufo_render_rays: ray range [%lld,%lld) outside the %dx%d grid", (long long)ray_begin,
+                (long long)(ray_begin + n_rays), sc->d.H, sc->d.W);
+  if (n_rays == 0) return UFO_OK;
+  if (int e = check_device()) return e;
+  int dev = 0;
+  UFO_CUDA(cudaGetDevice(&dev));
+  if (dev != sc->device || dev != w->device) return fail(UFO_EINVAL, "ufo_render_rays: handles belong to another device");
+  cudaStream_t st = (cudaStream_t)stream_;
+  int sms = 0;
+  UFO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  std::lock_guard<std::mutex> lock(sc->mu);
+  if (mode == UFO_MODE_TC)
+    return tc_render_rays(sc->d, w->tc, w->inv_s, ray_idx, ray_begin, n_rays, u_coarse, u_fine, u_stride, out, taps, sms, dev, st);
+  const int chunk = fp32_chunk_rays();
+  if (int e = ws_ensure(sc, n_rays < chunk ? n_rays : chunk)) return e;
+  for (int64_t off = 0; off < n_rays; off += chunk) {
+    const int R = (int)((n_rays - off) < chunk ? (n_rays - off) : chunk);
+    if (int e = render_chunk_fp32(sc, w, ray_idx, ray_begin, R, u_coarse, u_fine, u_stride, off, out, taps, sms, st)) return e;
+  }
+  return UFO_OK;
+}
+
+extern "C" int ufo_render_rays_host(const UfoScene* sc, const UfoWeights* w, int64_t ray_begin, int32_t n_rays,
+                                    const float* u_c_host, const float* u_f_host, int32_t mode, float* depth_z_host,
+                                    float* rgb_host, void* stream_) {
+  if (!sc || !w || !u_c_host || !u_f_host || !depth_z_host || !rgb_host) return fail(UFO_EINVAL, "ufo_render_rays_host: null argument");
+  if (n_rays <= 0) return n_rays == 0 ? UFO_OK : fail(UFO_EINVAL, "ufo_render_rays_host: n_rays < 0");
+  if (int e = check_device()) return e;
+  cudaStream_t st = (cudaStream_t)stream_;
+  {
+    std::lock_guard<std::mutex> lock(sc->mu);
+    if (sc->u_cap < (size_t)n_rays) {
+      cudaFree(sc->u_dev); cudaFree(sc->out_dev);
+      sc->u_dev = nullptr; sc->out_dev = nullptr; sc->u_cap = 0;
+      UFO_CUDA(cudaMalloc(&sc->u_dev, sizeof(float) * 2 * kNC * (size_t)n_rays));
+      UFO_CUDA(cudaMalloc(&sc->out_dev, sizeof(float) * 5 * (size_t)n_rays));
+      sc->u_cap = (size_t)n_rays;
+    }
+  }
+  float* u_c = sc->u_dev;
+  float* u_f = sc->u_dev + (size_t)kNC * n_rays;
+  UFO_CUDA(cudaMemcpyAsync(u_c, u_c_host, sizeof(float) * kNC * (size_t)n_rays, cudaMemcpyHostToDevice, st));
+  UFO_CUDA(cudaMemcpyAsync(u_f, u_f_host, sizeof(float) * kNC * (size_t)n_rays, cudaMemcpyHostToDevice, st));
+  UfoRenderOut o{};
+  o.depth_z = sc->out_dev;
+  o.rgb = sc->out_dev + n_rays;
+  o.depth = sc->out_dev + 4 * (size_t)n_rays;
+  if (int e = ufo_render_rays(sc, w, nullptr, ray_begin, n_rays, u_c, u_f, n_rays, mode, &o, nullptr, stream_)) return e;
+  UFO_CUDA(cudaMemcpyAsync(depth_z_host, o.depth_z, sizeof(float) * n_rays, cudaMemcpyDeviceToHost, st));
+  UFO_CUDA(cudaMemcpyAsync(rgb_host, o.rgb, sizeof(float) * 3 * (size_t)n_rays, cudaMemcpyDeviceToHost, st));
+  UFO_CUDA(cudaStreamSynchronize(st));
+  return UFO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel 1: cost volume
+// ------------------------------------------------------------------------------------------------
+namespace {
+void mat4_mul(const double* a, const double* b, double* c) {
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      double s = 0;
+      for (int k = 0; k < 4; ++k) s += a[i * 4 + k] * b[k * 4 + j];
+      c[i * 4 + j] = s;
+    }
+}
+bool mat4_inv(const double* m, double* inv) {
+  double a[4][8];
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) { a[i][j] = m[i * 4 + j]; a[i][j + 4] = (i == j) ? 1.0 : 0.0; }
+  for (int c = 0; c < 4; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < 4; ++r) if (std::fabs(a[r][c]) > std::fabs(a[piv][c])) piv = r;
+    if (std::fabs(a[piv][c]) < 1e-300) return false;
+    if (piv != c) for (int j = 0; j < 8; ++j) std::swap(a[c][j], a[piv][j]);
+    const double d = a[c][c];
+    for (int j = 0; j < 8; ++j) a[c][j] /= d;
+    for (int r = 0; r < 4; ++r) if (r != c) { const double f = a[r][c]; for (int j = 0; j < 8; ++j) a[r][j] -= f * a[c][j]; }
+  }
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) inv[i * 4 + j] = a[i][j + 4];
+  return true;
+}
+// proj [2][4][4] -> K[:3,:3] @ E[:3,:4] in the top rows of E  (TransMVSNet.py:77-80)
+void fold_proj(const float* p, double* out) {
+  const float* E = p;
+  const float* K = p + 16;
+  for (int i = 0; i < 16; ++i) out[i] = E[i];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 4; ++j) {
+      double s = 0;
+      for (int k = 0; k < 3; ++k) s += (double)K[i * 4 + k] * (double)E[k * 4 + j];
+      out[i * 4 + j] = s;
+    }
+}
+}  // namespace
+
+template <int C, int D>
+static int launch_costvol(const float* ref, const float* const* src_dev, const WarpMats* mats, const float* hyp, const float* vw_in,
+                          const PixelwiseDev& pw, int N, int V, int h, int w, float* sim, float* vw_out, cudaStream_t st) {
+  const long long threads = (long long)N * h * w * (C / 4);
+  if (vw_in)
+    k_costvol<C, D, false><<<cdiv(threads, 256), 256, 0, st>>>(ref, src_dev, mats, hyp, vw_in, pw, N, V, h, w, sim, vw_out);
+  else
+    k_costvol<C, D, true><<<cdiv(threads, 256), 256, 0, st>>>(ref, src_dev, mats, hyp, vw_in, pw, N, V, h, w, sim, vw_out);
+  UFO_LAUNCH_CHECK();
+  return UFO_OK;
+}
+
+extern "C" int ufo_costvolume_stage(const float* const* feats, int32_t N, int32_t V, int32_t C, int32_t h, int32_t w, int32_t D,
+                                    const float* proj, const float* hyp, const float* vw_in, const UfoPixelwiseNet* pwn,
+                                    float* sim, float* vw_out, void* stream_) {
+  if (!feats || !proj || !hyp || !sim) return fail(UFO_EINVAL, "ufo_costvolume_stage: null argument");
+  if (!vw_in && (!pwn || !vw_out)) return fail(UFO_EINVAL, "ufo_costvolume_stage: stage 1 needs the pixel-wise net and view_w_out");
+  if (V < 2 || V > UFO_MAX_VIEWS || N < 1) return fail(UFO_EINVAL, "ufo_costvolume_stage: bad N/V");
+  if (!((C == 32 && D == 48) || (C == 16 && D == 32) || (C == 8 && D == 8)))
+    return fail(UFO_EINVAL, "ufo_costvolume_stage: unsupported (C=%d, D=%d); cascade is (32,48),(16,32),(8,8)", C, D);
+  if (int e = check_device()) return e;
+  cudaStream_t st = (cudaStream_t)stream_;
+  // warp matrices in double on the host
+  std::vector<WarpMats> mats((size_t)N * (V - 1));
+  for (int n = 0; n < N; ++n) {
+    double ref[16], ref_inv[16];
+    fold_proj(proj + ((size_t)n * V + 0) * 32, ref);
+    if (!mat4_inv(ref, ref_inv)) return fail(UFO_EINVAL, "ufo_costvolume_stage: singular reference projection");
+    for (int i = 1; i < V; ++i) {
+      double src[16], T[16];
+      fold_proj(proj + ((size_t)n * V + i) * 32, src);
+      mat4_mul(src, ref_inv, T);
+      WarpMats& m = mats[(size_t)n * (V - 1) + (i - 1)];
+      for (int a = 0; a < 3; ++a) {
+        for (int b = 0; b < 3; ++b) m.r[a * 3 + b] = (float)T[a * 4 + b];
+        m.t[a] = (float)T[a * 4 + 3];
+      }
+    }
+  }
+  PixelwiseDev pw{};
+  if (!vw_in) {
+    for (int c = 0; c < 16; ++c) {
+      const double s = (double)pwn->bn0_w[c] / std::sqrt((double)pwn->bn0_var[c] + 1e-5);
+      pw.s0[c] = (float)(s * pwn->conv0_w[c]);
+      pw.t0[c] = (float)(pwn->bn0_b[c] - s * pwn->bn0_mean[c]);
+    }
+    for (int o = 0; o < 8; ++o) {
+      const double s = (double)pwn->bn1_w[o] / std::sqrt((double)pwn->bn1_var[o] + 1e-5);
+      for (int c = 0; c < 16; ++c) pw.w1[o][c] = (float)(s * pwn->conv1_w[o * 16 + c]);
+      pw.t1[o] = (float)(pwn->bn1_b[o] - s * pwn->bn1_mean[o]);
+      pw.w2[o] = pwn->conv2_w[o];
+    }
+    pw.b2 = pwn->conv2_b;
+  }
+  const size_t fl = (size_t)N * C * h * w;
+  float* cl = nullptr;          // V channel-last copies
+  WarpMats* mats_dev = nullptr;
+  const float** src_ptrs_dev = nullptr;
+  UFO_CUDA(cudaMallocAsync((void**)&cl, sizeof(float) * fl * V, st));
+  UFO_CUDA(cudaMallocAsync((void**)&mats_dev, sizeof(WarpMats) * mats.size(), st));
+  UFO_CUDA(cudaMallocAsync((void**)&src_ptrs_dev, sizeof(float*) * (V - 1), st));
+  int e = UFO_OK;
+  for (int i = 0; i < V && !e; ++i) {
+    if (C == 32) e = repack_cl<32>(feats[i], cl + fl * i, (long long)h * w, N, st);
+    else if (C == 16) e = repack_cl<16>(feats[i], cl + fl * i, (long long)h * w, N, st);
+    else e = repack_cl<8>(feats[i], cl + fl * i, (long long)h * w, N, st);
+  }
+  std::vector<const float*> src_ptrs(V - 1);
+  for (int i = 1; i < V; ++i) src_ptrs[i - 1] = cl + fl * i;
+  if (!e) {
+    cudaError_t ce = cudaMemcpyAsync(mats_dev, mats.data(), sizeof(WarpMats) * mats.size(), cudaMemcpyHostToDevice, st);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(src_ptrs_dev, src_ptrs.data(), sizeof(float*) * (V - 1), cudaMemcpyHostToDevice, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);  // host vectors go out of scope below
+    if (ce != cudaSuccess) e = fail(UFO_ECUDA, "ufo_costvolume_stage: %s", cudaGetErrorString(ce));
+  }
+  if (!e) {
+    if (C == 32) e = launch_costvol<32, 48>(cl, src_ptrs_dev, mats_dev, hyp, vw_in, pw, N, V, h, w, sim, vw_out, st);
+    else if (C == 16) e = launch_costvol<16, 32>(cl, src_ptrs_dev, mats_dev, hyp, vw_in, pw, N, V, h, w, sim, vw_out, st);
+    else e = launch_costvol<8, 8>(cl, src_ptrs_dev, mats_dev, hyp, vw_in, pw, N, V, h, w, sim, vw_out, st);
+  }
+  cudaFreeAsync(cl, st);
+  cudaFreeAsync(mats_dev, st);
+  cudaFreeAsync((void*)src_ptrs_dev, st);
+  return e;
+}

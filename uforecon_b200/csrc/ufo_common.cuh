@@ -1,0 +1,71 @@
+// Shared definitions of the UFORecon B200 hot-path library (device structs, error plumbing).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/uforecon_b200.h"
+
+namespace ufo {
+
+constexpr int kFeatC = 32;   // FPN feature / match-map channels   (ray_transformer.py:91)
+constexpr int kVolC = 8;     // CostRegNetWeight feature channels  (feature_volume.py:110)
+constexpr int kDView = 80;   // 32 + 24 + 16 + 8                   (ray_transformer.py:135)
+constexpr int kDRay = 88;    // kDView + 8 order PE                (ray_transformer.py:138)
+constexpr int kHeads = 8;
+constexpr int kNC = UFO_N_COARSE;
+constexpr int kNS = UFO_N_SAMPLES;
+constexpr int kMaxV = UFO_MAX_VIEWS;
+
+// Per-view-set constants, passed to kernels by value (fits the 4 KB parameter space).
+struct SceneDev {
+  int nv, H, W, h, w;
+  int vd[3], vh[3], vw[3];
+  const float* feat_cl;         // [NV][h][w][32]
+  const float4* rgbd_cl;        // [NV][H][W] (r,g,b,mvs_depth)
+  const float* match_cl;        // [NV][NV-1][h][w][32]
+  const float* vol_feat_cl[3];  // [NV][D][hs][ws][8]
+  const float* vol_w[3];        // [NV][D][hs][ws]
+  const float* ray_d;           // [3][H*W]
+  const float* cam_ray_d;       // [3][H*W]
+  float P[kMaxV][12];           // rows 0..2 of the world->NDC matrices (source_poses)
+  float w2c_z[kMaxV][4];        // third row of the scaled w2c (camera-space z of a point)
+  float cam_o[kMaxV][3];        // source camera centres  (source_poses_inv[:, :3, 3])
+  float ref_o[3];               // render camera centre   (ref_pose_inv[:3, 3])
+  float ray_o[3];
+  float near0, far0;            // near_fars[0]  (model.py:328,416-421 use view 0 for every view)
+};
+
+extern thread_local char g_err[512];
+extern std::atomic<long long> g_launches;
+
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define UFO_CUDA(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess)                                                                   \
+      return ::ufo::fail(UFO_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+#define UFO_LAUNCH_CHECK()                                                                   \
+  do {                                                                                       \
+    ::ufo::g_launches.fetch_add(1, std::memory_order_relaxed);                               \
+    cudaError_t _e = cudaGetLastError();                                                     \
+    if (_e != cudaSuccess)                                                                   \
+      return ::ufo::fail(UFO_ECUDA, "%s:%d kernel launch: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+  } while (0)
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace ufo

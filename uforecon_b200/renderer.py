@@ -1,0 +1,281 @@
+"""Host-side mirror of the reference's per-ray rendering interface on top of the C ABI.
+
+Same names, argument meaning and return values as the reference methods this replaces:
+
+* ``UFOReconRenderer.infer(batch, ray_idx, source_imgs_feat, feature_volume, extract_geometry=True,
+  match_feature=...)`` -> ``(srdf, points_x_all, depth, rgb)``       code1/model.py:393-478
+* ``UFOReconRenderer.render_depth_map(...)`` - the chunk loop of ``extract_geometry``
+  (code1/model.py:814-826): depth map in mm ``[H, W]`` and colour ``[H, W, 3]``.
+
+PyTorch is only plumbing here (device memory, streams); all arithmetic of the path runs in
+``libuforecon_b200.so``.  Nothing in this module falls back to PyTorch ops or to ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import UFO_MODE_FP32, UFO_MODE_TC, UFO_N_COARSE, UFO_N_FINE, UFO_N_SAMPLES
+
+RT = "ray_transformer."
+STAGES = ("stage1", "stage2", "stage3")
+
+
+def _host_f32(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to("cpu", torch.float32).contiguous()
+
+
+def _dev_f32(t: torch.Tensor, device: torch.device) -> torch.Tensor:
+    return t.detach().to(device, torch.float32).contiguous()
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class HotPathWeights:
+    """``ray_transformer.*`` + ``deviation_network.variance`` packed on the device."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device: Optional[torch.device] = None):
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else "cuda")
+        keep: List[torch.Tensor] = []
+
+        def p(name: str) -> int:
+            if name not in state_dict:
+                raise KeyError(f"state dict lacks hot-path key {name!r}")
+            t = _host_f32(state_dict[name])
+            keep.append(t)
+            return t.data_ptr()
+
+        def loftr(prefix: str) -> _lib.UfoLoftrLayer:
+            l = _lib.UfoLoftrLayer()
+            l.q, l.k, l.v = p(prefix + "q_proj.weight"), p(prefix + "k_proj.weight"), p(prefix + "v_proj.weight")
+            l.merge, l.mlp0, l.mlp2 = p(prefix + "merge.weight"), p(prefix + "mlp.0.weight"), p(prefix + "mlp.2.weight")
+            l.norm1_w, l.norm1_b = p(prefix + "norm1.weight"), p(prefix + "norm1.bias")
+            l.norm2_w, l.norm2_b = p(prefix + "norm2.weight"), p(prefix + "norm2.bias")
+            return l
+
+        def mlp3(prefix: str) -> _lib.UfoMlp3:
+            m = _lib.UfoMlp3()
+            m.w0, m.b0 = p(prefix + "0.weight"), p(prefix + "0.bias")
+            m.w2, m.b2 = p(prefix + "2.weight"), p(prefix + "2.bias")
+            m.w4, m.b4 = p(prefix + "4.weight"), p(prefix + "4.bias")
+            return m
+
+        d = _lib.UfoWeightsDesc()
+        d.view = loftr(RT + "density_view_transformer.layers.0.")
+        d.ray = loftr(RT + "density_ray_transformer.layers.0.")
+        d.pre_sim = mlp3(RT + "pre_sim_mlp.")
+        d.density = mlp3(RT + "DensityMLP.")
+        d.radiance = mlp3(RT + "linear_radianceweight_1_softmax.")
+        d.view_token = p(RT + "viewToken.view_token")
+        d.depth_freqs = p(RT + "depthcode._freqs")
+        d.depth_phases = p(RT + "depthcode._phases")
+        d.variance = float(state_dict["deviation_network.variance"])
+        self.handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ufo_weights_create(C.byref(d), C.byref(self.handle), _stream_ptr(self.device)))
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle:
+            self.lib.ufo_weights_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Scene:
+    """One view set: what ``extract_geometry`` assembles before its chunk loop (model.py:777-808)."""
+
+    def __init__(self, batch: Dict[str, torch.Tensor], source_imgs_feat: torch.Tensor,
+                 feature_volume: Dict[str, Dict[str, torch.Tensor]], match_feature: Sequence[torch.Tensor],
+                 device: Optional[torch.device] = None):
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else "cuda")
+        if source_imgs_feat.shape[0] != 1:
+            raise ValueError("batch size must be 1 (reference eval DataLoader, main.py:159-162)")
+        B, NV, _, H, W = batch["source_imgs"].shape
+        _, _, FC, h, w = source_imgs_feat.shape
+        if FC != 32:
+            raise ValueError(f"feature maps must have 32 channels, got {FC}")
+        if tuple(match_feature[0].shape) != (1, NV, (NV - 1) * 32, h, w):
+            raise ValueError(f"match_feature[0] shape {tuple(match_feature[0].shape)} != {(1, NV, (NV - 1) * 32, h, w)}")
+        if "depth_info" not in batch:
+            raise KeyError("batch['depth_info'] missing (set by extract_geometry, model.py:806-808)")
+        dev = self.device
+        keep = []
+
+        def dv(t):
+            t = _dev_f32(t, dev)
+            keep.append(t)
+            return t.data_ptr()
+
+        def hv(t):
+            t = _host_f32(t)
+            keep.append(t)
+            return t.data_ptr()
+
+        d = _lib.UfoSceneDesc()
+        d.n_views, d.img_h, d.img_w, d.feat_h, d.feat_w = NV, H, W, h, w
+        d.source_imgs = dv(batch["source_imgs"][0])
+        d.img_feats = dv(source_imgs_feat[0])
+        d.depth_info = dv(batch["depth_info"][0])
+        d.match_feats = dv(match_feature[0][0])
+        for i, st in enumerate(STAGES):
+            fv, wv = feature_volume[st]["feature_volume"], feature_volume[st]["weight_volume"]
+            if fv.shape[0] != NV or fv.shape[1] != 8 or wv.shape[1] != 1:
+                raise ValueError(f"{st}: feature/weight volume shapes {tuple(fv.shape)} / {tuple(wv.shape)}")
+            d.vol_feat[i], d.vol_weight[i] = dv(fv), dv(wv)
+            d.vol_d[i], d.vol_h[i], d.vol_w[i] = fv.shape[2], fv.shape[3], fv.shape[4]
+        d.source_poses = hv(batch["source_poses"][0])
+        d.source_poses_inv = hv(batch["source_poses_inv"][0])
+        d.ref_pose_inv = hv(batch["ref_pose_inv"][0])
+        d.w2cs = hv(batch["w2cs"][0])
+        d.near_fars = hv(batch["near_fars"][0])
+        d.ray_o = hv(batch["ray_o"][0])
+        d.ray_d = dv(batch["ray_d"][0])
+        d.cam_ray_d = dv(batch["cam_ray_d"][0])
+        self.n_views, self.H, self.W = NV, H, W
+        self.scale = float(batch["scale_mat"][0][0, 0]) if "scale_mat" in batch else 1.0
+        self.handle = C.c_void_p()
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.ufo_scene_create(C.byref(d), C.byref(self.handle), _stream_ptr(dev)))
+            torch.cuda.current_stream(dev).synchronize()   # inputs in `keep` may be freed after this
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self.lib.ufo_scene_device_bytes(self.handle))
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle:
+            self.lib.ufo_scene_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+TAP_SHAPES = {
+    "z_coarse": lambda n, nv: (n, 64), "weight_coarse": lambda n, nv: (n, 64), "srdf_coarse": lambda n, nv: (n, 64),
+    "z_fine": lambda n, nv: (n, 64), "sim8": lambda n, nv: (n, 128, 8), "vol24": lambda n, nv: (n, 128, 24),
+    "tokens": lambda n, nv: (n, 128, nv, 80), "view_tok0": lambda n, nv: (n, 128, 80),
+    "ray_out": lambda n, nv: (n, 128, 88), "radiance": lambda n, nv: (n, 128, 3), "weight": lambda n, nv: (n, 128),
+}
+
+
+def draw_uniforms(n_rays: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The sampler draws of one reference ``infer`` call, from torch's global CPU generator and in the
+    reference's order: ``torch.rand(64, RN)`` (sampler.py:42) then ``torch.rand(64, RN)`` (sampler.py:86)."""
+    return torch.rand(UFO_N_COARSE, n_rays), torch.rand(UFO_N_FINE, n_rays)
+
+
+def render_rays(scene: Scene, weights: HotPathWeights, ray_idx: Optional[torch.Tensor], n_rays: int,
+                u_coarse: torch.Tensor, u_fine: torch.Tensor, mode: int = UFO_MODE_FP32, ray_begin: int = 0,
+                want: Sequence[str] = ("depth", "depth_z", "rgb"), taps: Sequence[str] = ()) -> Dict[str, torch.Tensor]:
+    """Thin wrapper of ``ufo_render_rays`` with device tensors; returns the requested outputs/taps."""
+    dev = scene.device
+    lib = scene.lib
+    u_c, u_f = _dev_f32(u_coarse, dev), _dev_f32(u_fine, dev)
+    if u_c.shape != (UFO_N_COARSE, u_c.shape[1]) or u_f.shape != u_c.shape or u_c.shape[1] < n_rays:
+        raise ValueError("u_coarse/u_fine must be [64, >=n_rays]")
+    shapes = {"depth": (n_rays,), "depth_z": (n_rays,), "rgb": (n_rays, 3), "srdf": (n_rays, UFO_N_SAMPLES),
+              "z": (n_rays, UFO_N_SAMPLES), "points": (n_rays, UFO_N_SAMPLES, 3)}
+    res: Dict[str, torch.Tensor] = {}
+    out = _lib.UfoRenderOut()
+    for k in want:
+        res[k] = torch.empty(shapes[k], dtype=torch.float32, device=dev)
+        setattr(out, k, res[k].data_ptr())
+    tp = _lib.UfoDebugTaps()
+    for k in taps:
+        res[k] = torch.empty(TAP_SHAPES[k](n_rays, scene.n_views), dtype=torch.float32, device=dev)
+        setattr(tp, k, res[k].data_ptr())
+    idx_ptr = None
+    if ray_idx is not None:
+        ray_idx = ray_idx.detach().to(dev, torch.int64).contiguous()
+        if ray_idx.numel() != n_rays:
+            raise ValueError("ray_idx size != n_rays")
+        idx_ptr = ray_idx.data_ptr()
+    with torch.cuda.device(dev):
+        _lib.check(lib.ufo_render_rays(scene.handle, weights.handle, idx_ptr, ray_begin, n_rays, u_c.data_ptr(), u_f.data_ptr(),
+                                       u_c.shape[1], mode, C.byref(out), C.byref(tp) if taps else None, _stream_ptr(dev)))
+    return res
+
+
+class UFOReconRenderer:
+    """Drop-in for the reference model's ray-rendering methods (see module docstring)."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device=None, mode: int = UFO_MODE_TC,
+                 test_ray_num: int = 800):
+        self.device = torch.device(device if device is not None else "cuda")
+        self.weights = HotPathWeights(state_dict, self.device)
+        self.mode = mode
+        self.test_ray_num = test_ray_num
+        self._scene_key = None
+        self._scene: Optional[Scene] = None
+
+    def _scene_for(self, batch, source_imgs_feat, feature_volume, match_feature) -> Scene:
+        key = (source_imgs_feat.data_ptr(), match_feature[0].data_ptr(), batch["source_poses"].data_ptr(),
+               feature_volume["stage3"]["feature_volume"].data_ptr())
+        if self._scene is None or key != self._scene_key:
+            if self._scene is not None:
+                self._scene.close()
+            self._scene = Scene(batch, source_imgs_feat, feature_volume, match_feature, self.device)
+            self._scene_key = key
+        return self._scene
+
+    def infer(self, batch, ray_idx, source_imgs_feat, feature_volume=None, extract_geometry=False, match_feature=None,
+              ray_idx_all=None, is_train=True):
+        """``UFORecon.infer`` in its ``extract_geometry=True`` form (code1/model.py:393-478).
+
+        ray_idx [1, RN] int64.  Uniforms are drawn here from torch's global CPU generator exactly as the
+        reference's samplers do, so ``torch.manual_seed(s)`` gives the same sample positions.
+        Returns (srdf [1,RN,128], points_x_all [1,RN,128,3], depth [1,RN], rgb [1,RN,3]).
+        """
+        if not extract_geometry:
+            raise NotImplementedError("only the extract_geometry=True form of infer is on the hot path")
+        if feature_volume is None or match_feature is None:
+            raise ValueError("feature_volume and match_feature are required (canonical flag set, SURVEY.md section 5)")
+        scene = self._scene_for(batch, source_imgs_feat, feature_volume, match_feature)
+        RN = ray_idx.shape[1]
+        u_c, u_f = draw_uniforms(RN)
+        r = render_rays(scene, self.weights, ray_idx[0], RN, u_c, u_f, self.mode, want=("depth", "rgb", "srdf", "points"))
+        return r["srdf"][None], r["points"][None], r["depth"][None], r["rgb"][None]
+
+    def render_depth_map(self, batch, source_imgs_feat, feature_volume, match_feature, chunk: Optional[int] = None):
+        """The chunk loop of ``extract_geometry`` (model.py:814-826): depth [H,W] in mm, rgb [H,W,3].
+
+        With ``chunk=None`` the whole ray grid goes through one library call per ``test_ray_num`` draw group
+        only logically: uniforms are still drawn per reference chunk (800 rays) so that results do not
+        depend on how the library tiles the work.
+        """
+        scene = self._scene_for(batch, source_imgs_feat, feature_volume, match_feature)
+        H, W = scene.H, scene.W
+        n = H * W
+        step = self.test_ray_num
+        u_c = torch.empty(UFO_N_COARSE, n, pin_memory=True)
+        u_f = torch.empty(UFO_N_FINE, n, pin_memory=True)
+        for s in range(0, n, step):                     # reference draw order: per 800-ray chunk, coarse then fine
+            e = min(n, s + step)
+            a, b = draw_uniforms(e - s)
+            u_c[:, s:e] = a
+            u_f[:, s:e] = b
+        r = render_rays(scene, self.weights, None, n, u_c, u_f, self.mode, ray_begin=0, want=("depth_z", "rgb"))
+        depth_mm = (r["depth_z"] * scene.scale).view(H, W)
+        return depth_mm, r["rgb"].view(H, W, 3)
+
+    def close(self):
+        if self._scene is not None:
+            self._scene.close()
+            self._scene = None
+        self.weights.close()
