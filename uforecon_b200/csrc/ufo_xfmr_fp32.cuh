@@ -168,22 +168,29 @@ struct Mlp3Dev {
 };
 
 // Generic 3-layer ReLU MLP evaluated by one thread; weights read through the read-only path
-// (all threads of a warp read the same address).
-template <int IN, int H1, int H2, int OUT>
-__device__ __forceinline__ void mlp3_eval(const Mlp3Dev& w, const float* x, float* out) {
+// (all threads of a warp read the same address).  The input is IN_A values read in place from `xa`
+// (global memory, L1-resident across the H1 passes) followed by IN_B values held in registers.
+template <int IN_A, int IN_B, int H1, int H2, int OUT>
+__device__ __forceinline__ void mlp3_eval(const Mlp3Dev& w, const float* __restrict__ xa, const float* xb, float* out) {
+  constexpr int IN = IN_A + IN_B;
   float h1[H1];
-#pragma unroll 4
-  for (int o = 0; o < H1; ++o) {
-    float a = __ldg(w.b0 + o);
-    for (int i = 0; i < IN; ++i) a = fmaf(x[i], __ldg(w.w0 + o * IN + i), a);
-    h1[o] = fmaxf(a, 0.f);
+#pragma unroll
+  for (int o = 0; o < H1; ++o) h1[o] = __ldg(w.b0 + o);
+  for (int i = 0; i < IN_A; ++i) {
+    const float xv = xa[i];
+#pragma unroll
+    for (int o = 0; o < H1; ++o) h1[o] = fmaf(xv, __ldg(w.w0 + o * IN + i), h1[o]);
   }
+#pragma unroll
+  for (int i = 0; i < IN_B; ++i)
+#pragma unroll
+    for (int o = 0; o < H1; ++o) h1[o] = fmaf(xb[i], __ldg(w.w0 + o * IN + IN_A + i), h1[o]);
   float h2[H2];
-#pragma unroll 4
+#pragma unroll
   for (int o = 0; o < H2; ++o) {
     float a = __ldg(w.b2 + o);
 #pragma unroll
-    for (int i = 0; i < H1; ++i) a = fmaf(h1[i], __ldg(w.w2 + o * H1 + i), a);
+    for (int i = 0; i < H1; ++i) a = fmaf(fmaxf(h1[i], 0.f), __ldg(w.w2 + o * H1 + i), a);
     h2[o] = fmaxf(a, 0.f);
   }
 #pragma unroll
@@ -202,10 +209,8 @@ __global__ void __launch_bounds__(128) k_presim(const float* __restrict__ sim8, 
                                                float* __restrict__ XV) {
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
-  float x[8], o[16];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) x[i] = sim8[p * 8 + i];
-  mlp3_eval<8, 32, 32, 16>(w, x, o);
+  float o[16];
+  mlp3_eval<8, 0, 32, 32, 16>(w, sim8 + p * 8, nullptr, o);
   float* xv = XV + p * L * 160;
   for (int c = 0; c < kDView; ++c) xv[c] = __ldg(view_token + c);
   for (int n = 1; n < L; ++n)
@@ -229,10 +234,8 @@ __global__ void __launch_bounds__(128) k_density(const float* __restrict__ ROUT,
                                                 float* __restrict__ srdf) {
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
-  float x[kDRay], o[1];
-#pragma unroll 8
-  for (int i = 0; i < kDRay; ++i) x[i] = ROUT[p * kDRay + i];
-  mlp3_eval<kDRay, 32, 16, 1>(w, x, o);
+  float o[1];
+  mlp3_eval<kDRay, 0, 32, 16, 1>(w, ROUT + p * kDRay, nullptr, o);
   srdf[p] = o[0];
 }
 
@@ -247,13 +250,10 @@ __global__ void __launch_bounds__(128) k_radiance(const float* __restrict__ VOUT
   float om[kMaxV];
   float mx = -INFINITY;
   for (int n = 0; n < NV; ++n) {
-    float x[kDView + 3], o[1];
-    const float* vf = VOUT + (p * L + n + 1) * kDView;
-#pragma unroll 8
-    for (int i = 0; i < kDView; ++i) x[i] = vf[i];
+    float o[1];
     const float4 d = dirs[p * NV + n];
-    x[kDView] = d.x; x[kDView + 1] = d.y; x[kDView + 2] = d.z;
-    mlp3_eval<kDView + 3, 16, 8, 1>(w, x, o);
+    const float xb[3] = {d.x, d.y, d.z};
+    mlp3_eval<kDView, 3, 16, 8, 1>(w, VOUT + (p * L + n + 1) * kDView, xb, o);
     om[n] = (rgbm[p * NV + n].w == 0.f) ? -1e9f : o[0];     // ray_transformer.py:316
     mx = fmaxf(mx, om[n]);
   }
