@@ -200,6 +200,12 @@ int ufo_costvolume_stage(const float* const* feats, int32_t n_rot, int32_t n_vie
                          const float* depth_hyp, const float* view_w_in, const UfoPixelwiseNet* pw,
                          float* similarity, float* view_w_out, void* stream);
 
+/* Diagnostics: one-CTA tcgen05 GEMM through the library's own operand-staging and descriptor helpers
+ * (csrc/ufo_umma.cuh).  mode 0: D[128,N] = A[128,K] . B[N,K]^T; mode 1: D = At[K,128]^T . Bt[K,N].
+ * All [dev] fp32; operands are rounded to fp16 (bf16 != 0: bf16) on the way to shared memory. */
+int ufo_debug_umma_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t mode,
+                            int32_t bf16, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -69,7 +69,7 @@ class UfoPixelwiseNet(C.Structure):
 EXPORTS = (
     "ufo_abi_version", "ufo_last_error", "ufo_device_info", "ufo_weights_create", "ufo_weights_destroy",
     "ufo_scene_create", "ufo_scene_destroy", "ufo_scene_device_bytes", "ufo_render_rays", "ufo_render_rays_host",
-    "ufo_launch_count", "ufo_costvolume_stage",
+    "ufo_launch_count", "ufo_costvolume_stage", "ufo_debug_umma_selftest",
 )
 
 _lib = None
@@ -107,6 +107,8 @@ def load() -> C.CDLL:
     lib.ufo_costvolume_stage.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                          C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(UfoPixelwiseNet),
                                          C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ufo_debug_umma_selftest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                            C.c_void_p]
     if lib.ufo_abi_version() != 1:
         raise UfoError(f"ABI version mismatch: library {lib.ufo_abi_version()} != binding 1")
     _lib = lib

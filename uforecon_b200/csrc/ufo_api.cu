@@ -11,6 +11,7 @@
 #include "ufo_sampler_render.cuh"
 #include "ufo_xfmr_fp32.cuh"
 #include "ufo_xfmr_tc.cuh"
+#include "ufo_umma_selftest.cuh"
 
 namespace ufo {
 thread_local char g_err[512] = "";
@@ -660,4 +661,26 @@ extern "C" int ufo_costvolume_stage(const float* const* feats, int32_t N, int32_
   cudaFreeAsync(mats_dev, st);
   cudaFreeAsync((void*)src_ptrs_dev, st);
   return e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// diagnostics
+// ------------------------------------------------------------------------------------------------
+extern "C" int ufo_debug_umma_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t mode, int32_t bf16,
+                                       void* stream_) {
+  if (!A || !B || !D) return fail(UFO_EINVAL, "ufo_debug_umma_selftest: null argument");
+  if (N < 16 || N > 256 || N % 16 || K < 16 || K > 256 || K % 16 || (mode == 1 && K > 128))
+    return fail(UFO_EINVAL, "ufo_debug_umma_selftest: need 16<=N<=256, 16<=K<=256 (<=128 in mode 1), multiples of 16");
+  if (int e = check_device()) return e;
+  cudaStream_t st = (cudaStream_t)stream_;
+  const size_t smem = (size_t)128 * 256 * 2 + (size_t)256 * 256 * 2;
+  if (bf16) {
+    UFO_CUDA(cudaFuncSetAttribute(k_umma_selftest<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_umma_selftest<true><<<1, 128, smem, st>>>(A, B, D, N, K, mode);
+  } else {
+    UFO_CUDA(cudaFuncSetAttribute(k_umma_selftest<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_umma_selftest<false><<<1, 128, smem, st>>>(A, B, D, N, K, mode);
+  }
+  UFO_LAUNCH_CHECK();
+  return UFO_OK;
 }

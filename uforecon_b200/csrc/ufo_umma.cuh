@@ -1,0 +1,145 @@
+// tcgen05 / TMEM / mbarrier primitives for sm_100a (inline PTX; no CUTLASS dependency).
+//
+// Operand layouts used throughout (no swizzle, "interleaved" canonical UMMA layout): a 16-bit operand
+// tile is a grid of 8x8 core matrices, each 128 contiguous bytes (8 rows of 16 bytes).
+//   K-major  operand [R rows][K]: core (r/8, k/8) at  (k/8)*LBO + (r/8)*SBO, row r%8 at +16*(r%8)
+//   MN-major operand [K][R]     : core (r/8, k/8) at  (k/8)*LBO + (r/8)*SBO, k-row k%8 at +16*(k%8)
+// With the tile stored chunk-major (all row groups of k-chunk 0, then k-chunk 1, ...):
+//   SBO = 128 B, LBO = (R/8)*128 B, and a thread that owns row r writes its 8 consecutive K values of
+//   chunk c as ONE 16-byte store at  c*LBO + (r/8)*128 + (r%8)*16  (a warp covers 512 contiguous bytes).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+
+namespace ufo {
+namespace umma {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier -------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- TMEM -----------------------------------------------------------------------------------
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// whole warp; ncols power of two >= 32.  The allocated base address is written to *dst_smem.
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// 16 consecutive fp32 columns of this thread's TMEM lane (warp w reads lanes 32*(w%4)..+31).
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- descriptors ------------------------------------------------------------------------------
+// Shared-memory matrix descriptor, SWIZZLE_NONE (layout_type 0), descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+enum : uint32_t { kFmtF16 = 0, kFmtBF16 = 1 };
+
+// Instruction descriptor of tcgen05.mma.kind::f16 with fp32 accumulation.
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t M, uint32_t N, uint32_t fmt, bool a_mn_major, bool b_mn_major) {
+  return (1u << 4)                      // c_format = F32
+         | (fmt << 7) | (fmt << 10)     // a_format, b_format
+         | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16)
+         | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] . B[smem]   (one K=16 step).  Issued by ONE thread.
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// Arrive on `bar` when all previously issued MMAs of this thread have completed (implies
+// tcgen05.fence::before_thread_sync).  Issued by ONE thread.
+__device__ __forceinline__ void commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- operand staging helpers ------------------------------------------------------------------
+template <bool kBF16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if (kBF16) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  } else {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+}
+
+// Byte offset of the 16-byte piece (row r, k-chunk c) inside a chunk-major tile with `rows` rows.
+__device__ __forceinline__ uint32_t tile_off(uint32_t rows, uint32_t r, uint32_t c) {
+  return c * (rows * 16u) + (r >> 3) * 128u + (r & 7u) * 16u;
+}
+
+// Issue the K-loop of one GEMM: D[128 x N] = A[128 x K] . B[N x K]^T, both K-major chunk-major tiles.
+// a_base/b_base are shared-memory byte addresses of the tiles; a_rows/b_rows their row counts.
+__device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_base, uint32_t a_rows, uint32_t b_base, uint32_t b_rows,
+                                           uint32_t k_chunks /* K/8 */, uint32_t idesc, uint32_t accumulate_first) {
+  const uint32_t a_lbo = a_rows * 16u, b_lbo = b_rows * 16u;
+  for (uint32_t c = 0; c < k_chunks; c += 2) {
+    const uint64_t ad = make_smem_desc(a_base + c * a_lbo, a_lbo, 128u);
+    const uint64_t bd = make_smem_desc(b_base + c * b_lbo, b_lbo, 128u);
+    mma_f16(tmem_d, ad, bd, idesc, (c > 0) ? 1u : accumulate_first);
+  }
+}
+
+}  // namespace umma
+}  // namespace ufo
