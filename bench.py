@@ -1,0 +1,450 @@
+#!/usr/bin/env python
+"""bench.py - rays/s and seconds per DTU-shaped depth map of the per-ray rendering hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--mode tc|fp32]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one full depth map of the workload (BASELINE.json configs[1]: 1600x1216 ray grid, 3 source
+views, unfavourable set 1/16/36, 64+64 samples per ray) rendered by ``ufo_render_rays`` - i.e. everything
+``UFORecon.infer`` does for every pixel ray (code1/model.py:393-478) - from synthetic DTU-format inputs
+(``uforecon_b200.synthetic``) and a synthetic checkpoint with the reference's state-dict layout.
+
+* ``value``  rays/s, whole job, inputs (scene tensors AND sampler uniforms) resident in HBM.
+* ``e2e``    the same metric through ``ufo_render_rays_host``: sampler uniforms start in pinned HOST memory,
+             depth/rgb end in pinned HOST memory, copies inside the timed region.
+* ``roofline``      the dominant kernel of the timed region against its roofline.
+* ``cpu_baseline``  the CPU restatement of the reference (oracle/) timed on this box's host cores on a bounded
+                    sample of the same workload (N=1 only).
+* N>1: weak scaling - every rank renders its own full depth map (BASELINE configs[4]: image-sharded sweep);
+  ``sec_per_depth_map_sharded`` additionally times ONE depth map with its rows sharded over the N ranks
+  (configs[2]) including the gather of depth/rgb to rank 0.
+
+``--impl reference`` times the reference's CPU implementation of the same path on the host cores (the
+oracle port - /root/reference does not exist on the GPU box) and prints the same JSON line shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "rays_per_sec"
+UNIT = "rays/s"
+
+
+# --------------------------------------------------------------------------------------------------
+# algorithmic work per unit
+# --------------------------------------------------------------------------------------------------
+def flops_per_point(nv: int) -> dict:
+    """Algorithmic FLOPs (2 x MAC, true K, no padding) per sample point of the transformer stage."""
+    d, dr = 80, 88
+    loftr = lambda dd: 2 * (3 * dd * dd + dd * dd + 4 * dd * dd + 2 * dd * dd)      # qkv, merge, mlp0, mlp2
+    attn = lambda dd: 2 * 2 * dd * (dd // 8)                                          # K^T V and Q.KV per token
+    view = (loftr(d) + attn(d)) * (nv + 1)
+    ray = loftr(dr) + attn(dr)
+    presim = 2 * (8 * 32 + 32 * 32 + 32 * 16)
+    density = 2 * (88 * 32 + 32 * 16 + 16)
+    radiance = 2 * (83 * 16 + 16 * 8 + 8) * nv
+    return {"view": view, "ray": ray, "presim": presim, "density": density, "radiance": radiance,
+            "total": view + ray + presim + density + radiance}
+
+
+def tap_bytes_per_point(nv: int) -> int:
+    """Bytes of texel/voxel taps one point reads (L2/L1 level)."""
+    return 512 * nv * (nv - 1) + 864 * nv + 512 * nv + 48 * nv + 16 * nv
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples nvidia-smi SM clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------------
+# workload
+# --------------------------------------------------------------------------------------------------
+VIEW_SETS = {"unfavorable": [1, 16, 36], "favorable": [23, 24, 33]}
+
+
+def view_ids(name: str, nv: int):
+    from uforecon_b200 import synthetic
+    if name in VIEW_SETS and nv == 3:
+        return VIEW_SETS[name]
+    return synthetic.TEN_VIEW_LIST[:nv]
+
+
+def build_workload(args):
+    from uforecon_b200 import checkpoint, synthetic
+    W, H = args.width, args.height
+    views = view_ids(args.views, args.nv)
+    sd, src = checkpoint.load_hot_path_state(os.path.join(ROOT, "pretrained", "uforecon.ckpt"))
+    batch = synthetic.make_batch(views, (W, H))
+    scene = synthetic.make_scene(batch)
+    batch["depth_info"] = scene["depth_info"]
+    return batch, scene, sd, src, views
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return {"hbm_gbs": j["hbm_gbs"], "tf_burst": j["bf16_tflops"], "tf_sustained": j["bf16_tflops_sustained"], "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback"}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU leg (oracle port of the reference) - used by cpu_baseline and by --impl reference
+# --------------------------------------------------------------------------------------------------
+def cpu_chunks(batch, scene, sd, n_chunks: int, chunk: int = 800, warm: int = 1):
+    """Times ``n_chunks`` calls of the reference's ``infer`` restatement on ``chunk`` rays each (the reference's
+    own chunking: --test_ray_num 800, script/eval_dtu_unfavorable.sh).  Returns (rays/s, seconds, rays)."""
+    from oracle import uforecon_oracle as orc      # checker / CPU baseline only
+    from uforecon_b200 import synthetic
+    H, W = batch["source_imgs"].shape[-2:]
+    total = H * W
+    times = []
+    with torch.no_grad():
+        for i in range(warm + n_chunks):
+            # chunks spread over the image so that the sample sees centre and border rays
+            begin = (total // (warm + n_chunks + 1)) * (i + 1)
+            ray_idx = torch.arange(begin, min(begin + chunk, total))
+            u_c, u_f = synthetic.sampler_uniforms(len(ray_idx), seed=100 + i)
+            t0 = time.perf_counter()
+            orc.infer(batch, scene, sd, ray_idx, u_c, u_f)
+            dt = time.perf_counter() - t0
+            if i >= warm:
+                times.append((dt, len(ray_idx)))
+    secs = sum(t for t, _ in times)
+    rays = sum(n for _, n in times)
+    return rays / secs, secs, rays
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation (oracle port) on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    batch, scene, sd, src, views = build_workload(args)
+    chunk = 800
+    per_step = max(1, args.ref_chunks)
+    # warm-up steps and timed steps are both bounded samples (per_step chunks of 800 rays)
+    for _ in range(min(args.warmup, 1)):
+        cpu_chunks(batch, scene, sd, 1, chunk, warm=0)
+    t_all, r_all = 0.0, 0
+    for _ in range(args.steps):
+        _, secs, rays = cpu_chunks(batch, scene, sd, per_step, chunk, warm=0)
+        t_all += secs
+        r_all += rays
+    val = r_all / t_all
+    H, W = batch["source_imgs"].shape[-2:]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "sec_per_depth_map": H * W / val,
+        "config": workload_config(args, views, src, "cpu-fp32"),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{args.steps} steps x {per_step} chunks of {chunk} rays of the same workload "
+                                   f"(reference chunking --test_ray_num 800), extrapolated"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, views, ckpt_src, mode_name):
+    return {"workload": f"DTU-shaped {args.width}x{args.height} ray grid, {args.nv} source views {views} "
+                        f"({args.views}), 64 coarse + 64 importance samples/ray, full depth-map render "
+                        f"(BASELINE configs[1])",
+            "rays_per_depth_map": args.width * args.height, "n_views": args.nv, "mode": mode_name,
+            "checkpoint": ckpt_src,
+            "l2": "inputs larger than L2 (scene tensors 4.2 GB at 1600x1216 vs 126 MB L2); no explicit flush",
+            "parallelism": f"dp{args.gpus} (one full depth map per rank per step; no collective in the timed region)"}
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    from uforecon_b200 import _lib, dist as ufodist
+    from uforecon_b200.renderer import HotPathWeights, Scene, render_rays
+    import ctypes as C
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if world != args.gpus and rank == 0:
+        print(f"bench.py: warning --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+
+    import __graft_entry__ as ge
+    ge.build()
+    lib = _lib.load()
+    mode = {"fp32": _lib.UFO_MODE_FP32, "tc": _lib.UFO_MODE_TC, "tc16": getattr(_lib, "UFO_MODE_TC_F16", 2)}[args.mode]
+
+    t0 = time.time()
+    batch, scene, sd, ckpt_src, views = build_workload(args)
+    weights = HotPathWeights(sd, dev)
+    sc = Scene(batch, scene["source_imgs_feat"], scene["feature_volume"], scene["match_feature"], dev)
+    H, W = sc.H, sc.W
+    n_rays = H * W
+    setup_s = time.time() - t0
+
+    # sampler uniforms (FixedSampler / ImportanceSampler draws of the reference, sampler.py:42,86):
+    # pinned host copies for the e2e leg, device copies for the resident leg
+    gen = torch.Generator().manual_seed(1234 + rank)
+    u_c_host = torch.rand(64, n_rays, generator=gen).pin_memory()
+    u_f_host = torch.rand(64, n_rays, generator=gen).pin_memory()
+    u_c, u_f = u_c_host.to(dev), u_f_host.to(dev)
+    out_depth = torch.empty(n_rays, device=dev)
+    out_depthz = torch.empty(n_rays, device=dev)
+    out_rgb = torch.empty(n_rays, 3, device=dev)
+    out = _lib.UfoRenderOut()
+    out.depth, out.depth_z, out.rgb = out_depth.data_ptr(), out_depthz.data_ptr(), out_rgb.data_ptr()
+    stream = torch.cuda.current_stream(dev)
+
+    def step_resident(begin=0, n=n_rays):
+        _lib.check(lib.ufo_render_rays(sc.handle, weights.handle, None, begin, n, u_c.data_ptr() + 4 * begin,
+                                       u_f.data_ptr() + 4 * begin, n_rays, mode, C.byref(out), None, stream.cuda_stream))
+
+    depth_host = torch.empty(n_rays).pin_memory()
+    rgb_host = torch.empty(n_rays, 3).pin_memory()
+
+    def step_e2e():
+        _lib.check(lib.ufo_render_rays_host(sc.handle, weights.handle, 0, n_rays, u_c_host.data_ptr(), u_f_host.data_ptr(),
+                                            mode, depth_host.data_ptr(), rgb_host.data_ptr(), stream.cuda_stream))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+
+    # ---- timed region: K steps, CUDA events on the launching stream, per-kernel event brackets on
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = lib.ufo_launch_count()
+    _lib.profile_begin()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+    e1.record(stream)
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    prof = _lib.profile_end(256)
+    launches = lib.ufo_launch_count() - launches0
+    clk = clocks.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    value = world * n_rays * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: host buffers, copies inside the timed region
+    for _ in range(1):
+        step_e2e()
+    barrier()
+    k_e2e = max(1, min(args.steps, args.e2e_steps))
+    e0.record(stream)
+    for _ in range(k_e2e):
+        step_e2e()
+    e1.record(stream)
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = world * n_rays * k_e2e / (ms_e2e * 1e-3)
+
+    # ---- strong-scaling extra: ONE depth map with rows sharded over the ranks (+ gather to rank 0)
+    sharded_s = None
+    begin, n_mine = ufodist.shard_rows(H, W, world, rank)
+    counts = ufodist.shard_counts(H, W, world)
+    for it in range(3):
+        barrier()
+        e0.record(stream)
+        step_resident(begin, n_mine)
+        got = ufodist.gather_depth_rgb(out_depthz[:n_mine], out_rgb[:n_mine], counts) if world > 1 else None
+        e1.record(stream)
+        barrier()
+        sharded_s = max_over_ranks(e0.elapsed_time(e1)) * 1e-3
+    del got
+
+    # ---- roofline of the dominant kernel
+    pk = peaks()
+    roof = roofline_from_profile(prof, args, n_rays, pk)
+
+    # ---- CPU baseline (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        v, secs, rays = cpu_chunks(batch, scene, sd, args.cpu_chunks)
+        cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{args.cpu_chunks} chunks of 800 rays of the same workload after 1 warm-up chunk "
+                         f"({secs:.1f} s of CPU work, oracle restatement of the reference, torch CPU fp32)",
+               "sec_per_depth_map_extrapolated": n_rays / v}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp32": "f32", "tc": "bf16", "tc16": "f16"}[args.mode], "data": "synthetic",
+            "sec_per_depth_map": ms_step * 1e-3,
+            "sec_per_depth_map_sharded": sharded_s,
+            "config": workload_config(args, views, ckpt_src, args.mode),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * 64 * 4 * n_rays,
+                    "d2h_bytes_per_step": 16 * n_rays, "steps": k_e2e,
+                    "api": "ufo_render_rays_host (pinned host uniforms in, pinned host depth/rgb out)"},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": roof,
+            "kernels": [{"name": n, "launches": c, "ms": round(ms, 3)} for n, c, ms in sorted(prof, key=lambda x: -x[2])[:12]],
+            "cpu_baseline": cpu,
+            "setup_s": round(setup_s, 1),
+            "scene_device_bytes": sc.device_bytes,
+        }
+        print(json.dumps(line), flush=True)
+    sc.close()
+    weights.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def roofline_from_profile(prof, args, n_rays, pk):
+    """Roofline entry of the kernel with the largest share of the timed region."""
+    if not prof:
+        return None
+    total_ms = sum(ms for _, _, ms in prof)
+    name, cnt, ms = max(prof, key=lambda x: x[2])
+    nv = args.nv
+    fl = flops_per_point(nv)
+    pts = n_rays * 192 * args.steps           # sample-point evaluations in the timed region (64 coarse + 128 fine)
+    avg_s = ms * 1e-3 / cnt
+    work = None
+    bound, unit = "tensor", "TFLOP/s"
+    if name.startswith("k_view_tc"):
+        work = pts * (fl["view"] + fl["radiance"])
+    elif name.startswith("k_ray_tc"):
+        work = pts * (fl["ray"] + fl["density"])
+    elif name.startswith("k_linear<"):
+        k, n = [int(x) for x in name[len("k_linear<"):-1].split(",")]
+        rows = {80: pts * (nv + 1), 160: pts * (nv + 1), 88: pts, 176: pts}[k]
+        work = 2.0 * rows * k * n
+    elif name.startswith("k_gather"):
+        bound, unit = "hbm", "GB/s"
+        work = pts * tap_bytes_per_point(nv)
+    if work is None:
+        return {"kernel": name, "share_of_step": ms / total_ms, "bound": None, "achieved": None, "peak": None,
+                "unit": None, "frac": None, "traffic": None}
+    per_launch = work / cnt
+    if bound == "tensor":
+        achieved = per_launch / avg_s / 1e12
+        peak = pk["tf_sustained"]
+    else:
+        achieved = per_launch / avg_s / 1e9
+        peak = pk["hbm_gbs"]
+    return {"kernel": name, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
+            "traffic": None, "peak_source": pk["src"] + (" (sustained bf16)" if bound == "tensor" else " (copy)"),
+            "launches": cnt, "avg_launch_ms": avg_s * 1e3, "share_of_step": ms / total_ms,
+            "algorithmic_work_per_launch": per_launch}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default=os.environ.get("UFO_BENCH_MODE", "fp32"), choices=["fp32", "tc", "tc16"])
+    ap.add_argument("--width", type=int, default=int(os.environ.get("UFO_BENCH_W", "1600")))
+    ap.add_argument("--height", type=int, default=int(os.environ.get("UFO_BENCH_H", "1216")))
+    ap.add_argument("--nv", type=int, default=3)
+    ap.add_argument("--views", default="unfavorable", choices=["unfavorable", "favorable"])
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-chunks", type=int, default=4)
+    ap.add_argument("--ref-chunks", type=int, default=2, help="--impl reference: 800-ray chunks per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -175,6 +175,18 @@ int ufo_render_rays_host(const UfoScene* scene, const UfoWeights* weights, int64
 /* Number of kernel launches issued by this library since process start (bench.py's gpu_launches). */
 int64_t ufo_launch_count(void);
 
+/* Per-kernel device-time accounting for bench.py's roofline: between ufo_profile_begin() and
+ * ufo_profile_end() every kernel the library launches is bracketed by CUDA events on its launching
+ * stream; ufo_profile_end() synchronises the device and returns, per kernel name, the launch count and
+ * the summed event time.  Process-global; not meant to be left on in production. */
+typedef struct {
+  char name[48];
+  int64_t launches;
+  double ms;
+} UfoProfileEntry;
+int ufo_profile_begin(void);
+int ufo_profile_end(UfoProfileEntry* out, int32_t cap, int32_t* n_out);
+
 /* Cost-volume build of one cascade stage for all N reference rotations (replaces the loop of
  * DepthNet.forward, TransMVSNet.py:76-100, with homo_warping_trans, fmt/module.py:329-367 and
  * PixelwiseNet, TransMVSNet.py:23-41; the 3-D CNN regulariser stays in PyTorch).

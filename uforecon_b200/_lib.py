@@ -65,11 +65,15 @@ class UfoPixelwiseNet(C.Structure):
                                            "bn1_mean", "bn1_var", "conv2_w")] + [("conv2_b", C.c_float)]
 
 
+class UfoProfileEntry(C.Structure):
+    _fields_ = [("name", C.c_char * 48), ("launches", C.c_int64), ("ms", C.c_double)]
+
+
 #: every symbol the header declares (tests check the built library exports all of them)
 EXPORTS = (
     "ufo_abi_version", "ufo_last_error", "ufo_device_info", "ufo_weights_create", "ufo_weights_destroy",
     "ufo_scene_create", "ufo_scene_destroy", "ufo_scene_device_bytes", "ufo_render_rays", "ufo_render_rays_host",
-    "ufo_launch_count", "ufo_costvolume_stage", "ufo_debug_umma_selftest",
+    "ufo_launch_count", "ufo_costvolume_stage", "ufo_debug_umma_selftest", "ufo_profile_begin", "ufo_profile_end",
 )
 
 _lib = None
@@ -109,6 +113,7 @@ def load() -> C.CDLL:
                                          C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ufo_debug_umma_selftest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                             C.c_void_p]
+    lib.ufo_profile_end.argtypes = [C.POINTER(UfoProfileEntry), C.c_int32, C.POINTER(C.c_int32)]
     if lib.ufo_abi_version() != 1:
         raise UfoError(f"ABI version mismatch: library {lib.ufo_abi_version()} != binding 1")
     _lib = lib
@@ -119,3 +124,15 @@ def check(rc: int) -> None:
     if rc != 0:
         msg = load().ufo_last_error().decode(errors="replace")
         raise UfoError(f"libuforecon_b200 error {rc}: {msg}")
+
+
+def profile_begin() -> None:
+    check(load().ufo_profile_begin())
+
+
+def profile_end(cap: int = 256):
+    """-> list of (kernel name, launches, summed device ms) since ``profile_begin``."""
+    arr = (UfoProfileEntry * cap)()
+    n = C.c_int32()
+    check(load().ufo_profile_end(arr, cap, C.byref(n)))
+    return [(arr[i].name.decode(), int(arr[i].launches), float(arr[i].ms)) for i in range(n.value)]

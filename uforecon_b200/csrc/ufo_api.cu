@@ -1,7 +1,9 @@
 // C-ABI entry points of libuforecon_b200.so (declared in include/uforecon_b200.h).
 #include <cmath>
 #include <cstdlib>
+#include <map>
 #include <mutex>
+#include <string>
 #include <vector>
 
 #include "ufo_common.cuh"
@@ -16,6 +18,31 @@
 namespace ufo {
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+
+// ---- per-kernel device-time accounting -----------------------------------------------------------
+std::atomic<int> g_prof_on{0};
+namespace {
+struct ProfRec { const char* name; cudaEvent_t e0, e1; };
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof_recs;
+std::vector<cudaEvent_t> g_prof_pool;   // recycled events
+cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+}  // namespace
+void prof_open(const char* name, cudaStream_t st) {
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  ProfRec r{name, prof_event(), prof_event()};
+  cudaEventRecord(r.e0, st);
+  g_prof_recs.push_back(r);
+}
+void prof_close(cudaStream_t st) {
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  if (!g_prof_recs.empty()) cudaEventRecord(g_prof_recs.back().e1, st);
+}
 }  // namespace ufo
 
 using namespace ufo;
@@ -212,8 +239,7 @@ extern "C" void ufo_weights_destroy(UfoWeights* w) {
 template <int C>
 static int repack_cl(const float* in, float* out, long long S, int N, cudaStream_t st) {
   dim3 grid(cdiv(S, 32), N);
-  k_nchw_to_nhwc<C><<<grid, 256, 0, st>>>(in, out, S);
-  UFO_LAUNCH_CHECK();
+  UFO_KERNEL("k_nchw_to_nhwc<C>", st, k_nchw_to_nhwc<C><<<grid, 256, 0, st>>>(in, out, S));
   return UFO_OK;
 }
 
@@ -249,8 +275,7 @@ extern "C" int ufo_scene_create(const UfoSceneDesc* d, UfoScene** out, void* str
   if ((e = dalloc(sizeof(float) * nv * (nv - 1) * hw * kFeatC, (void**)&match_cl))) { ufo_scene_destroy(sc); return e; }
   if ((e = repack_cl<kFeatC>(d->img_feats, feat_cl, hw, nv, st))) { ufo_scene_destroy(sc); return e; }
   if ((e = repack_cl<kFeatC>(d->match_feats, match_cl, hw, nv * (nv - 1), st))) { ufo_scene_destroy(sc); return e; }
-  k_pack_rgbd<<<cdiv(HW * nv, 256), 256, 0, st>>>(d->source_imgs, d->depth_info, rgbd, HW, nv);
-  UFO_LAUNCH_CHECK();
+  UFO_KERNEL("k_pack_rgbd", st, k_pack_rgbd<<<cdiv(HW * nv, 256), 256, 0, st>>>(d->source_imgs, d->depth_info, rgbd, HW, nv));
   D.feat_cl = feat_cl; D.rgbd_cl = rgbd; D.match_cl = match_cl;
   for (int s = 0; s < 3; ++s) {
     D.vd[s] = d->vol_d[s]; D.vh[s] = d->vol_h[s]; D.vw[s] = d->vol_w[s];
@@ -342,8 +367,9 @@ static int launch_linear(const float* X, int ldx, const float* W, float* Y, int 
   }
   const long long tiles = (M + 63) / 64;
   const int grid = (int)(tiles < sms ? tiles : sms);
-  k_linear<K, N, R><<<grid, 256, smem, st>>>(X, ldx, W, Y, ldy, M);
-  UFO_LAUNCH_CHECK();
+  static char name[40] = "";
+  if (!name[0]) snprintf(name, sizeof(name), "k_linear<%d,%d>", K, N);
+  UFO_KERNEL(name, st, k_linear<K, N, R><<<grid, 256, smem, st>>>(X, ldx, W, Y, ldy, M));
   return UFO_OK;
 }
 
@@ -351,9 +377,8 @@ template <int NV>
 static int launch_gather(const UfoScene* sc, const UfoWeights* w, int R, int SN, const float* z, float* pts, cudaStream_t st) {
   const Workspace& ws = sc->ws;
   const long long P = (long long)R * SN;
-  k_gather<NV><<<cdiv(P, 32), 256, 0, st>>>(sc->d, ws.rayinfo, z, R, SN, w->freqs, w->phases, ws.XV, ws.sim8, ws.rgbm,
-                                           ws.dirs, pts);
-  UFO_LAUNCH_CHECK();
+  UFO_KERNEL("k_gather<NV>", st, k_gather<NV><<<cdiv(P, 32), 256, 0, st>>>(sc->d, ws.rayinfo, z, R, SN, w->freqs, w->phases, ws.XV, ws.sim8, ws.rgbm,
+                                           ws.dirs, pts));
   return UFO_OK;
 }
 
@@ -380,37 +405,27 @@ static int pass_fp32(const UfoScene* sc, const UfoWeights* w, int R, int SN, con
   const long long P = (long long)R * SN, MV = P * L;
   int e;
   if ((e = dispatch_gather(sc, w, R, SN, z, pts, st))) return e;
-  k_presim<<<cdiv(P, 128), 128, 0, st>>>(ws.sim8, w->pre_sim, w->view_token, L, P, ws.XV);
-  UFO_LAUNCH_CHECK();
+  UFO_KERNEL("k_presim", st, k_presim<<<cdiv(P, 128), 128, 0, st>>>(ws.sim8, w->pre_sim, w->view_token, L, P, ws.XV));
   // ---- view transformer (tokens = views of one sample point)
   if ((e = launch_linear<80, 240, false>(ws.XV, 160, w->view.qkv, ws.QKV, 240, MV, sms, st))) return e;
-  k_linattn<10><<<cdiv(P * kHeads, 128), 128, 0, st>>>(ws.QKV, ws.MSG, P, L);
-  UFO_LAUNCH_CHECK();
+  UFO_KERNEL("k_linattn<10>", st, k_linattn<10><<<cdiv(P * kHeads, 128), 128, 0, st>>>(ws.QKV, ws.MSG, P, L));
   if ((e = launch_linear<80, 80, false>(ws.MSG, 80, w->view.merge, ws.MRG, 80, MV, sms, st))) return e;
-  k_layernorm<80><<<cdiv(MV, 8), 256, 0, st>>>(ws.MRG, 80, w->view.n1w, w->view.n1b, nullptr, 0, ws.XV + 80, 160, MV);
-  UFO_LAUNCH_CHECK();
+  UFO_KERNEL("k_layernorm<80>", st, k_layernorm<80><<<cdiv(MV, 8), 256, 0, st>>>(ws.MRG, 80, w->view.n1w, w->view.n1b, nullptr, 0, ws.XV + 80, 160, MV));
   if ((e = launch_linear<160, 160, true>(ws.XV, 160, w->view.mlp0, ws.H1, 160, MV, sms, st))) return e;
   if ((e = launch_linear<160, 80, false>(ws.H1, 160, w->view.mlp2, ws.Y2, 80, MV, sms, st))) return e;
-  k_layernorm<80><<<cdiv(MV, 8), 256, 0, st>>>(ws.Y2, 80, w->view.n2w, w->view.n2b, ws.XV, 160, ws.VOUT, 80, MV);
-  UFO_LAUNCH_CHECK();
+  UFO_KERNEL("k_layernorm<80>", st, k_layernorm<80><<<cdiv(MV, 8), 256, 0, st>>>(ws.Y2, 80, w->view.n2w, w->view.n2b, ws.XV, 160, ws.VOUT, 80, MV));
   // ---- ray transformer (tokens = samples of one ray)
-  k_ray_tokens<<<cdiv(P * kDRay, 256), 256, 0, st>>>(ws.VOUT, L, SN, P, w->pe_table, ws.XR);
-  UFO_LAUNCH_CHECK();
+  UFO_KERNEL("k_ray_tokens", st, k_ray_tokens<<<cdiv(P * kDRay, 256), 256, 0, st>>>(ws.VOUT, L, SN, P, w->pe_table, ws.XR));
   if ((e = launch_linear<88, 264, false>(ws.XR, 176, w->ray.qkv, ws.QKV, 264, P, sms, st))) return e;
-  k_linattn<11><<<cdiv((long long)R * kHeads, 128), 128, 0, st>>>(ws.QKV, ws.MSG, R, SN);
-  UFO_LAUNCH_CHECK();
+  UFO_KERNEL("k_linattn<11>", st, k_linattn<11><<<cdiv((long long)R * kHeads, 128), 128, 0, st>>>(ws.QKV, ws.MSG, R, SN));
   if ((e = launch_linear<88, 88, false>(ws.MSG, 88, w->ray.merge, ws.MRG, 88, P, sms, st))) return e;
-  k_layernorm<88><<<cdiv(P, 8), 256, 0, st>>>(ws.MRG, 88, w->ray.n1w, w->ray.n1b, nullptr, 0, ws.XR + 88, 176, P);
-  UFO_LAUNCH_CHECK();
+  UFO_KERNEL("k_layernorm<88>", st, k_layernorm<88><<<cdiv(P, 8), 256, 0, st>>>(ws.MRG, 88, w->ray.n1w, w->ray.n1b, nullptr, 0, ws.XR + 88, 176, P));
   if ((e = launch_linear<176, 176, true>(ws.XR, 176, w->ray.mlp0, ws.H1, 176, P, sms, st))) return e;
   if ((e = launch_linear<176, 88, false>(ws.H1, 176, w->ray.mlp2, ws.Y2, 88, P, sms, st))) return e;
-  k_layernorm<88><<<cdiv(P, 8), 256, 0, st>>>(ws.Y2, 88, w->ray.n2w, w->ray.n2b, ws.XR, 176, ws.ROUT, 88, P);
-  UFO_LAUNCH_CHECK();
+  UFO_KERNEL("k_layernorm<88>", st, k_layernorm<88><<<cdiv(P, 8), 256, 0, st>>>(ws.Y2, 88, w->ray.n2w, w->ray.n2b, ws.XR, 176, ws.ROUT, 88, P));
   // ---- heads
-  k_density<<<cdiv(P, 128), 128, 0, st>>>(ws.ROUT, w->density, P, ws.srdf);
-  UFO_LAUNCH_CHECK();
-  k_radiance<<<cdiv(P, 128), 128, 0, st>>>(ws.VOUT, ws.dirs, ws.rgbm, w->radiance, nv, P, reinterpret_cast<float4*>(ws.radiance));
-  UFO_LAUNCH_CHECK();
+  UFO_KERNEL("k_density", st, k_density<<<cdiv(P, 128), 128, 0, st>>>(ws.ROUT, w->density, P, ws.srdf));
+  UFO_KERNEL("k_radiance", st, k_radiance<<<cdiv(P, 128), 128, 0, st>>>(ws.VOUT, ws.dirs, ws.rgbm, w->radiance, nv, P, reinterpret_cast<float4*>(ws.radiance)));
   return UFO_OK;
 }
 
@@ -423,8 +438,7 @@ __global__ void k_copy_strided(const float* __restrict__ src, int lds, float* __
 }
 
 static int copy_rows(const float* src, int lds, float* dst, int ldd, int cols, long long rows, cudaStream_t st) {
-  k_copy_strided<<<cdiv(rows * cols, 256), 256, 0, st>>>(src, lds, dst, ldd, cols, rows);
-  UFO_LAUNCH_CHECK();
+  UFO_KERNEL("k_copy_strided", st, k_copy_strided<<<cdiv(rows * cols, 256), 256, 0, st>>>(src, lds, dst, ldd, cols, rows));
   return UFO_OK;
 }
 
@@ -434,27 +448,22 @@ static int render_chunk_fp32(const UfoScene* sc, const UfoWeights* w, const int6
   const Workspace& ws = sc->ws;
   const int nv = sc->d.nv, L = nv + 1;
   int e;
-  k_ray_setup<<<cdiv(R, 256), 256, 0, st>>>(sc->d, (const long long*)(ray_idx ? ray_idx + off : nullptr), ray_begin + off, R, ws.rayinfo);
-  UFO_LAUNCH_CHECK();
-  k_coarse_z<<<cdiv((long long)R * kNC, 256), 256, 0, st>>>(ws.rayinfo, u_c + off, u_stride, R, ws.z_c);
-  UFO_LAUNCH_CHECK();
+  UFO_KERNEL("k_ray_setup", st, k_ray_setup<<<cdiv(R, 256), 256, 0, st>>>(sc->d, (const long long*)(ray_idx ? ray_idx + off : nullptr), ray_begin + off, R, ws.rayinfo));
+  UFO_KERNEL("k_coarse_z", st, k_coarse_z<<<cdiv((long long)R * kNC, 256), 256, 0, st>>>(ws.rayinfo, u_c + off, u_stride, R, ws.z_c));
   if ((e = pass_fp32(sc, w, R, kNC, ws.z_c, sms, nullptr, st))) return e;
-  k_render<kNC><<<cdiv(R, 8), 256, 0, st>>>(ws.z_c, ws.srdf, reinterpret_cast<const float4*>(ws.radiance), w->inv_s, R, ws.weight,
-                                          nullptr, nullptr, nullptr, ws.rayinfo);
-  UFO_LAUNCH_CHECK();
+  UFO_KERNEL("k_render<kNC>", st, k_render<kNC><<<cdiv(R, 8), 256, 0, st>>>(ws.z_c, ws.srdf, reinterpret_cast<const float4*>(ws.radiance), w->inv_s, R, ws.weight,
+                                          nullptr, nullptr, nullptr, ws.rayinfo));
   if (taps) {
     if (taps->z_coarse) UFO_CUDA(cudaMemcpyAsync(taps->z_coarse + off * kNC, ws.z_c, sizeof(float) * R * kNC, cudaMemcpyDeviceToDevice, st));
     if (taps->weight_coarse) UFO_CUDA(cudaMemcpyAsync(taps->weight_coarse + off * kNC, ws.weight, sizeof(float) * R * kNC, cudaMemcpyDeviceToDevice, st));
     if (taps->srdf_coarse) UFO_CUDA(cudaMemcpyAsync(taps->srdf_coarse + off * kNC, ws.srdf, sizeof(float) * R * kNC, cudaMemcpyDeviceToDevice, st));
   }
-  k_importance<<<cdiv(R, 8), 256, 0, st>>>(ws.weight, ws.z_c, u_f + off, u_stride, R, ws.z_fine, ws.z_all);
-  UFO_LAUNCH_CHECK();
+  UFO_KERNEL("k_importance", st, k_importance<<<cdiv(R, 8), 256, 0, st>>>(ws.weight, ws.z_c, u_f + off, u_stride, R, ws.z_fine, ws.z_all));
   float* pts = out->points ? out->points + off * kNS * 3 : nullptr;
   if ((e = pass_fp32(sc, w, R, kNS, ws.z_all, sms, pts, st))) return e;
-  k_render<kNS><<<cdiv(R, 8), 256, 0, st>>>(ws.z_all, ws.srdf, reinterpret_cast<const float4*>(ws.radiance), w->inv_s, R, ws.weight,
+  UFO_KERNEL("k_render<kNS>", st, k_render<kNS><<<cdiv(R, 8), 256, 0, st>>>(ws.z_all, ws.srdf, reinterpret_cast<const float4*>(ws.radiance), w->inv_s, R, ws.weight,
                                           out->depth ? out->depth + off : nullptr, out->rgb ? out->rgb + off * 3 : nullptr,
-                                          out->depth_z ? out->depth_z + off : nullptr, ws.rayinfo);
-  UFO_LAUNCH_CHECK();
+                                          out->depth_z ? out->depth_z + off : nullptr, ws.rayinfo));
   const long long P = (long long)R * kNS;
   if (out->srdf) UFO_CUDA(cudaMemcpyAsync(out->srdf + off * kNS, ws.srdf, sizeof(float) * P, cudaMemcpyDeviceToDevice, st));
   if (out->z) UFO_CUDA(cudaMemcpyAsync(out->z + off * kNS, ws.z_all, sizeof(float) * P, cudaMemcpyDeviceToDevice, st));
@@ -582,10 +591,9 @@ static int launch_costvol(const float* ref, const float* const* src_dev, const W
                           const PixelwiseDev& pw, int N, int V, int h, int w, float* sim, float* vw_out, cudaStream_t st) {
   const long long threads = (long long)N * h * w * (C / 4);
   if (vw_in)
-    k_costvol<C, D, false><<<cdiv(threads, 256), 256, 0, st>>>(ref, src_dev, mats, hyp, vw_in, pw, N, V, h, w, sim, vw_out);
+    UFO_KERNEL("k_costvol<C, D, false>", st, k_costvol<C, D, false><<<cdiv(threads, 256), 256, 0, st>>>(ref, src_dev, mats, hyp, vw_in, pw, N, V, h, w, sim, vw_out));
   else
-    k_costvol<C, D, true><<<cdiv(threads, 256), 256, 0, st>>>(ref, src_dev, mats, hyp, vw_in, pw, N, V, h, w, sim, vw_out);
-  UFO_LAUNCH_CHECK();
+    UFO_KERNEL("k_costvol<C, D, true>", st, k_costvol<C, D, true><<<cdiv(threads, 256), 256, 0, st>>>(ref, src_dev, mats, hyp, vw_in, pw, N, V, h, w, sim, vw_out));
   return UFO_OK;
 }
 
@@ -664,6 +672,49 @@ extern "C" int ufo_costvolume_stage(const float* const* feats, int32_t N, int32_
 }
 
 // ------------------------------------------------------------------------------------------------
+// profiling
+// ------------------------------------------------------------------------------------------------
+extern "C" int ufo_profile_begin(void) {
+  if (int e = check_device()) return e;
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  for (auto& r : g_prof_recs) { g_prof_pool.push_back(r.e0); g_prof_pool.push_back(r.e1); }
+  g_prof_recs.clear();
+  g_prof_on.store(1);
+  return UFO_OK;
+}
+
+extern "C" int ufo_profile_end(UfoProfileEntry* out, int32_t cap, int32_t* n_out) {
+  if (!n_out || (cap > 0 && !out)) return fail(UFO_EINVAL, "ufo_profile_end: null argument");
+  g_prof_on.store(0);
+  UFO_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  std::map<std::string, std::pair<long long, double>> acc;
+  std::vector<std::string> order;
+  for (auto& r : g_prof_recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) != cudaSuccess) { cudaGetLastError(); ms = 0.f; }
+    auto it = acc.find(r.name);
+    if (it == acc.end()) { order.push_back(r.name); it = acc.emplace(r.name, std::make_pair(0LL, 0.0)).first; }
+    it->second.first += 1;
+    it->second.second += (double)ms;
+    g_prof_pool.push_back(r.e0);
+    g_prof_pool.push_back(r.e1);
+  }
+  g_prof_recs.clear();
+  int n = 0;
+  for (auto& name : order) {
+    if (n >= cap) break;
+    UfoProfileEntry& e = out[n++];
+    memset(&e, 0, sizeof(e));
+    strncpy(e.name, name.c_str(), sizeof(e.name) - 1);
+    e.launches = acc[name].first;
+    e.ms = acc[name].second;
+  }
+  *n_out = n;
+  return UFO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // diagnostics
 // ------------------------------------------------------------------------------------------------
 extern "C" int ufo_debug_umma_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t mode, int32_t bf16,
@@ -676,11 +727,10 @@ extern "C" int ufo_debug_umma_selftest(const float* A, const float* B, float* D,
   const size_t smem = (size_t)128 * 256 * 2 + (size_t)256 * 256 * 2;
   if (bf16) {
     UFO_CUDA(cudaFuncSetAttribute(k_umma_selftest<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_umma_selftest<true><<<1, 128, smem, st>>>(A, B, D, N, K, mode);
+    UFO_KERNEL("k_umma_selftest<true>", st, k_umma_selftest<true><<<1, 128, smem, st>>>(A, B, D, N, K, mode));
   } else {
     UFO_CUDA(cudaFuncSetAttribute(k_umma_selftest<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_umma_selftest<false><<<1, 128, smem, st>>>(A, B, D, N, K, mode);
+    UFO_KERNEL("k_umma_selftest<false>", st, k_umma_selftest<false><<<1, 128, smem, st>>>(A, B, D, N, K, mode));
   }
-  UFO_LAUNCH_CHECK();
   return UFO_OK;
 }

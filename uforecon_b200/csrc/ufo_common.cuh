@@ -68,4 +68,30 @@ inline int fail(int code, const char* fmt, ...) {
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Per-kernel device-time accounting (ufo_profile_begin / ufo_profile_end): when enabled, a
+// ProfScope brackets one launch with CUDA events on the launching stream.
+struct ProfState;
+extern std::atomic<int> g_prof_on;
+void prof_open(const char* name, cudaStream_t st);
+void prof_close(cudaStream_t st);
+struct ProfScope {
+  cudaStream_t st;
+  bool on;
+  ProfScope(const char* name, cudaStream_t s) : st(s), on(g_prof_on.load(std::memory_order_relaxed) != 0) {
+    if (on) prof_open(name, st);
+  }
+  ~ProfScope() {
+    if (on) prof_close(st);
+  }
+};
+// Launch one kernel: optional event bracket, launch counter, launch-error check (returns on failure).
+#define UFO_KERNEL(name, st, ...)                 \
+  do {                                            \
+    {                                             \
+      ::ufo::ProfScope _ufo_prof_scope_(name, st); \
+      __VA_ARGS__;                                \
+    }                                             \
+    UFO_LAUNCH_CHECK();                           \
+  } while (0)
+
 }  // namespace ufo
