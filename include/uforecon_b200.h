@@ -51,7 +51,8 @@ enum {
 /* Transformer arithmetic of ufo_render_rays. */
 enum {
   UFO_MODE_FP32 = 0, /* CUDA-core fp32 everywhere (parity: 1e-5 relative)                        */
-  UFO_MODE_TC = 1    /* BF16 operands / FP32 accumulate on tcgen05 tensor cores for the GEMMs    */
+  UFO_MODE_TC = 1,   /* BF16 operands / FP32 accumulate on tcgen05 tensor cores for the GEMMs    */
+  UFO_MODE_TC_F16 = 2 /* same kernels with FP16 operands (3 more mantissa bits, narrower range)  */
 };
 
 typedef struct UfoScene UfoScene;     /* one view set: repacked source tensors + cameras        */

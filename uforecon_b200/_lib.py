@@ -18,6 +18,7 @@ UFO_N_FINE = 64
 UFO_N_SAMPLES = 128
 UFO_MODE_FP32 = 0
 UFO_MODE_TC = 1
+UFO_MODE_TC_F16 = 2
 
 c_float_p = C.POINTER(C.c_float)
 

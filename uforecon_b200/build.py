@@ -13,8 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libuforecon_b200.so")
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math=false",
-              "-Xcompiler", "-fPIC", "-shared"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+OBJ_DIR = os.path.join(HERE, "build")
 
 
 def _sources():
@@ -29,18 +29,36 @@ def needs_build() -> bool:
     return any(os.path.getmtime(s) > t for s in _sources() + [hdr])
 
 
+def _compile(args):
+    nvcc, src, obj, verbose = args
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    return src, r.returncode, r.stdout + r.stderr
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every .cu of csrc/ for sm_100a (one nvcc per translation unit, in parallel) and link the .so."""
     if not force and not needs_build():
         return OUT
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
-    cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, "ufo_api.cu"), "-o", OUT, "-lcudart"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    cus = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+    jobs = [(nvcc, os.path.join(CSRC, f), os.path.join(OBJ_DIR, f[:-3] + ".o"), verbose) for f in cus]
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
+        results = list(ex.map(_compile, jobs))
+    log = ""
+    for src, rc, out in results:
+        log += out
+        if rc != 0:
+            sys.stderr.write(out)
+            raise RuntimeError(f"nvcc failed on {os.path.basename(src)}")
+    r = subprocess.run([nvcc, "-shared", "-o", OUT] + [j[2] for j in jobs] + ["-lcudart"], capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed building libuforecon_b200.so")
+        raise RuntimeError("link of libuforecon_b200.so failed")
     if verbose:
-        sys.stderr.write(r.stderr)
+        sys.stderr.write(log)
     return OUT
 
 

@@ -12,7 +12,9 @@
 #include "ufo_repack.cuh"
 #include "ufo_sampler_render.cuh"
 #include "ufo_xfmr_fp32.cuh"
-#include "ufo_xfmr_tc.cuh"
+#include "ufo_handles.cuh"
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "ufo_umma_selftest.cuh"
 
 namespace ufo {
@@ -50,42 +52,6 @@ using namespace ufo;
 // ------------------------------------------------------------------------------------------------
 // handles
 // ------------------------------------------------------------------------------------------------
-struct LoftrDev {
-  const float *qkv, *merge, *mlp0, *mlp2, *n1w, *n1b, *n2w, *n2b;
-};
-
-struct UfoWeights {
-  int device = -1;
-  float* blob = nullptr;  // all fp32 tensors, one allocation
-  size_t blob_floats = 0;
-  LoftrDev view{}, ray{};
-  Mlp3Dev pre_sim{}, density{}, radiance{};
-  const float *view_token = nullptr, *freqs = nullptr, *phases = nullptr, *pe_table = nullptr;  // pe_table [128][8]
-  float inv_s = 1.f;
-  TcWeights tc;  // bf16 operand images for the tensor-core path
-};
-
-struct Workspace {
-  float* base = nullptr;
-  size_t floats = 0;
-  int cap_rays = 0, nv = 0;
-  float *rayinfo, *z_c, *z_all, *z_fine, *XV, *QKV, *MSG, *MRG, *H1, *Y2, *VOUT, *XR, *ROUT, *sim8, *radiance, *srdf,
-      *weight, *pts;
-  float4 *rgbm, *dirs;
-};
-
-struct UfoScene {
-  int device = -1;
-  SceneDev d{};
-  std::vector<void*> owned;
-  int64_t bytes = 0;
-  mutable Workspace ws;
-  mutable float* u_dev = nullptr;      // staging for ufo_render_rays_host
-  mutable float* out_dev = nullptr;
-  mutable size_t u_cap = 0;
-  mutable std::mutex mu;
-};
-
 static int check_device() {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
@@ -125,6 +91,90 @@ struct BlobBuilder {
   }
 };
 }  // namespace
+
+// ---- tensor-core operand images ------------------------------------------------------------------
+static uint16_t cvt16(float v, bool bf16) {
+  if (bf16) {
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    return *reinterpret_cast<uint16_t*>(&h);
+  }
+  __half h = __float2half_rn(v);
+  return *reinterpret_cast<uint16_t*>(&h);
+}
+static float back16(uint16_t u, bool bf16) {
+  if (bf16) return __bfloat162float(*reinterpret_cast<__nv_bfloat16*>(&u));
+  return __half2float(*reinterpret_cast<__half*>(&u));
+}
+// W [n_real][k_real] (row stride ldw) -> K-major chunk-major B operand image with n_pad rows, k_pad columns.
+// part 0: rounded value; part 1: rounded remainder (split precision).
+static void pack_b(uint8_t* img, const float* W, int n_real, int k_real, int ldw, int n_pad, int k_pad, bool bf16, int part = 0) {
+  uint16_t* o = reinterpret_cast<uint16_t*>(img);
+  for (int n = 0; n < n_pad; ++n)
+    for (int k = 0; k < k_pad; ++k) {
+      const float v = (n < n_real && k < k_real) ? W[(size_t)n * ldw + k] : 0.f;
+      uint16_t h = cvt16(v, bf16);
+      if (part == 1) h = cvt16(v - back16(h, bf16), bf16);
+      o[(size_t)(k / 8) * (n_pad * 8) + (size_t)n * 8 + (k % 8)] = h;
+    }
+}
+
+static int tc_weights_build(const UfoWeightsDesc* d, TcWeights* t, cudaStream_t st) {
+  for (int f = 0; f < 2; ++f) {
+    const bool bf16 = (f == 0);
+    std::vector<uint8_t> vi(tc::V_WEND, 0), ri(tc::RW_END, 0);
+    {  // view stage
+      std::vector<float> qkv((size_t)240 * 80);
+      memcpy(qkv.data(), d->view.q, sizeof(float) * 6400);
+      memcpy(qkv.data() + 6400, d->view.k, sizeof(float) * 6400);
+      memcpy(qkv.data() + 12800, d->view.v, sizeof(float) * 6400);
+      pack_b(vi.data() + tc::V_WQKV, qkv.data(), 240, 80, 80, 240, 80, bf16);
+      pack_b(vi.data() + tc::V_WMRG, d->view.merge, 80, 80, 80, 80, 80, bf16);
+      pack_b(vi.data() + tc::V_WML0, d->view.mlp0, 160, 160, 160, 160, 160, bf16);
+      pack_b(vi.data() + tc::V_WML2, d->view.mlp2, 80, 160, 160, 80, 160, bf16);
+      std::vector<float> rad((size_t)16 * 160);   // [W0x | W0x]: the head sees x + LN2 without forming the sum
+      for (int o = 0; o < 16; ++o)
+        for (int k = 0; k < 80; ++k) rad[o * 160 + k] = rad[o * 160 + 80 + k] = d->radiance.w0[o * 83 + k];
+      pack_b(vi.data() + tc::V_WRAD, rad.data(), 16, 160, 160, 16, 160, bf16);
+    }
+    {  // ray stage
+      std::vector<float> qkv((size_t)264 * 88);
+      memcpy(qkv.data(), d->ray.q, sizeof(float) * 7744);
+      memcpy(qkv.data() + 7744, d->ray.k, sizeof(float) * 7744);
+      memcpy(qkv.data() + 15488, d->ray.v, sizeof(float) * 7744);
+      pack_b(ri.data() + tc::RW_QKV, qkv.data(), 264, 88, 88, 272, 96, bf16);
+      pack_b(ri.data() + tc::RW_MRG, d->ray.merge, 88, 88, 88, 96, 96, bf16);
+      pack_b(ri.data() + tc::RW_ML0, d->ray.mlp0, 176, 176, 176, 176, 176, bf16);
+      pack_b(ri.data() + tc::RW_ML2, d->ray.mlp2, 88, 176, 176, 96, 176, bf16);
+      pack_b(ri.data() + tc::RW_DEN, d->density.w0, 32, 88, 88, 32, 96, bf16, 0);
+      pack_b(ri.data() + tc::RW_DEN + 32 * 96 * 2, d->density.w0, 32, 88, 88, 32, 96, bf16, 1);
+    }
+    UFO_CUDA(cudaMalloc(&t->view_img[f], vi.size()));
+    UFO_CUDA(cudaMalloc(&t->ray_img[f], ri.size()));
+    UFO_CUDA(cudaMemcpyAsync(t->view_img[f], vi.data(), vi.size(), cudaMemcpyHostToDevice, st));
+    UFO_CUDA(cudaMemcpyAsync(t->ray_img[f], ri.data(), ri.size(), cudaMemcpyHostToDevice, st));
+    UFO_CUDA(cudaStreamSynchronize(st));
+  }
+  ViewParams& vp = t->vp;
+  memcpy(vp.n1w, d->view.norm1_w, 320); memcpy(vp.n1b, d->view.norm1_b, 320);
+  memcpy(vp.n2w, d->view.norm2_w, 320); memcpy(vp.n2b, d->view.norm2_b, 320);
+  memcpy(vp.vtok, d->view_token, 320);
+  memcpy(vp.rb0, d->radiance.b0, 64);
+  for (int o = 0; o < 16; ++o)
+    for (int i = 0; i < 3; ++i) vp.rw0d[o][i] = d->radiance.w0[o * 83 + 80 + i];
+  memcpy(vp.rw2, d->radiance.w2, sizeof(vp.rw2));
+  memcpy(vp.rb2, d->radiance.b2, 32);
+  memcpy(vp.rw4, d->radiance.w4, 32);
+  vp.rb4 = d->radiance.b4[0];
+  RayParams& rp = t->rp;
+  memcpy(rp.n1w, d->ray.norm1_w, 352); memcpy(rp.n1b, d->ray.norm1_b, 352);
+  memcpy(rp.n2w, d->ray.norm2_w, 352); memcpy(rp.n2b, d->ray.norm2_b, 352);
+  memcpy(rp.db0, d->density.b0, 128);
+  memcpy(rp.dw2, d->density.w2, sizeof(rp.dw2));
+  memcpy(rp.db2, d->density.b2, 64);
+  memcpy(rp.dw4, d->density.w4, 64);
+  rp.db4 = d->density.b4[0];
+  return UFO_OK;
+}
 
 extern "C" int ufo_weights_create(const UfoWeightsDesc* d, UfoWeights** out, void* stream_) {
   if (!d || !out) return fail(UFO_EINVAL, "ufo_weights_create: null argument");
@@ -217,9 +267,8 @@ extern "C" int ufo_weights_create(const UfoWeightsDesc* d, UfoWeights** out, voi
   w->pe_table = w->blob + off[k++];
   // SingleVarianceNetwork: exp(10*variance) clipped to [1e-6, 1e6] (single_variance_network.py:11, renderer.py:25)
   w->inv_s = fminf(fmaxf(expf(d->variance * 10.0f), 1e-6f), 1e6f);
-  if (int e = tc_weights_create(d, &w->tc, stream)) {
-    cudaFree(w->blob);
-    delete w;
+  if (int e = tc_weights_build(d, &w->tc, stream)) {
+    ufo_weights_destroy(w);
     return e;
   }
   *out = w;
@@ -228,7 +277,7 @@ extern "C" int ufo_weights_create(const UfoWeightsDesc* d, UfoWeights** out, voi
 
 extern "C" void ufo_weights_destroy(UfoWeights* w) {
   if (!w) return;
-  tc_weights_destroy(&w->tc);
+  for (int f = 0; f < 2; ++f) { cudaFree(w->tc.view_img[f]); cudaFree(w->tc.ray_img[f]); }
   cudaFree(w->blob);
   delete w;
 }
@@ -314,9 +363,9 @@ extern "C" void ufo_scene_destroy(UfoScene* s) {
   if (!s) return;
   for (void* p : s->owned) cudaFree(p);
   cudaFree(s->ws.base);
+  cudaFree(s->tws.base);
   cudaFree(s->u_dev);
   cudaFree(s->out_dev);
-  tc_scene_release(s->device);
   delete s;
 }
 
@@ -483,12 +532,108 @@ static int render_chunk_fp32(const UfoScene* sc, const UfoWeights* w, const int6
   return UFO_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// tensor-core pipeline
+// ------------------------------------------------------------------------------------------------
+static int tc_chunk_rays(int sms) {
+  const char* e = getenv("UFO_TC_CHUNK");
+  int v = e ? atoi(e) : sms * 8;    // fine pass: 8 ray tiles per CTA; view stage: 32 point tiles per CTA (NV = 3)
+  return v < 2 ? 2 : v;
+}
+
+static int tws_ensure(const UfoScene* sc, int rays) {
+  TcWorkspace& w = sc->tws;
+  const int nv = sc->d.nv;
+  if (w.base && w.cap_rays >= rays && w.nv == nv) return UFO_OK;
+  if (w.base) { cudaFree(w.base); w.base = nullptr; }
+  const size_t P = (size_t)rays * kNS;
+  struct Item { void** p; size_t n; };
+  Item items[] = {
+      {(void**)&w.rayinfo, (size_t)rays * 8 * 4}, {(void**)&w.z_c, (size_t)rays * kNC * 4}, {(void**)&w.z_all, P * 4},
+      {(void**)&w.z_fine, (size_t)rays * kNC * 4}, {(void**)&w.vout0, P * kDView * 4}, {(void**)&w.srdf, P * 4},
+      {(void**)&w.weight, P * 4}, {(void**)&w.tok, P * nv * kDView * 2}, {(void**)&w.rgbm, P * nv * 16},
+      {(void**)&w.dirs, P * nv * 16}, {(void**)&w.radiance, P * 16}};
+  size_t total = 0;
+  for (auto& it : items) total += (it.n + 255) & ~size_t(255);
+  UFO_CUDA(cudaMalloc(&w.base, total));
+  size_t off = 0;
+  for (auto& it : items) { *it.p = w.base + off; off += (it.n + 255) & ~size_t(255); }
+  w.bytes = total; w.cap_rays = rays; w.nv = nv;
+  return UFO_OK;
+}
+
+namespace ufo {
+int tc_pass(bool bf16, const UfoScene* sc, const UfoWeights* w, int R, int SN, const float* z, float* sim8_tap, float* pts,
+            float* ray_out_tap, int sms, cudaStream_t st) {
+  const bool lo = sc->d.nv <= 5;
+  if (bf16) return lo ? tc_pass_bf16_lo(sc, w, R, SN, z, sim8_tap, pts, ray_out_tap, sms, st) : tc_pass_bf16_hi(sc, w, R, SN, z, sim8_tap, pts, ray_out_tap, sms, st);
+  return lo ? tc_pass_f16_lo(sc, w, R, SN, z, sim8_tap, pts, ray_out_tap, sms, st) : tc_pass_f16_hi(sc, w, R, SN, z, sim8_tap, pts, ray_out_tap, sms, st);
+}
+}  // namespace ufo
+
+// debug taps of the 16-bit token rows: tokens [P][NV][80] and vol24 [P][24] as fp32
+template <bool BF16>
+__global__ void k_tok_to_f32(const uint16_t* __restrict__ tok, int NV, long long P, float* __restrict__ tokens, float* __restrict__ vol24) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= P * NV * kDView) return;
+  const uint32_t u = tok[t];
+  const float v = BF16 ? __uint_as_float(u << 16) : __half2float(__ushort_as_half((unsigned short)u));
+  if (tokens) tokens[t] = v;
+  const int c = (int)(t % kDView);
+  const long long pn = t / kDView;
+  if (vol24 && (pn % NV) == 0 && c >= 32 && c < 56) vol24[(pn / NV) * 24 + (c - 32)] = v;
+}
+
+static int render_chunk_tc(const UfoScene* sc, const UfoWeights* w, bool bf16, const int64_t* ray_idx, int64_t ray_begin, int R,
+                           const float* u_c, const float* u_f, int64_t u_stride, int64_t off, const UfoRenderOut* out,
+                           const UfoDebugTaps* taps, int sms, cudaStream_t st) {
+  const TcWorkspace& ws = sc->tws;
+  const int nv = sc->d.nv;
+  int e;
+  UFO_KERNEL("k_ray_setup", st, k_ray_setup<<<cdiv(R, 256), 256, 0, st>>>(sc->d, (const long long*)(ray_idx ? ray_idx + off : nullptr), ray_begin + off, R, ws.rayinfo));
+  UFO_KERNEL("k_coarse_z", st, k_coarse_z<<<cdiv((long long)R * kNC, 256), 256, 0, st>>>(ws.rayinfo, u_c + off, u_stride, R, ws.z_c));
+  e = tc_pass(bf16, sc, w, R, kNC, ws.z_c, nullptr, nullptr, nullptr, sms, st);
+  if (e) return e;
+  UFO_KERNEL("k_render<kNC>", st, k_render<kNC><<<cdiv(R, 8), 256, 0, st>>>(ws.z_c, ws.srdf, ws.radiance, w->inv_s, R, ws.weight, nullptr, nullptr, nullptr, ws.rayinfo));
+  if (taps) {
+    if (taps->z_coarse) UFO_CUDA(cudaMemcpyAsync(taps->z_coarse + off * kNC, ws.z_c, sizeof(float) * R * kNC, cudaMemcpyDeviceToDevice, st));
+    if (taps->weight_coarse) UFO_CUDA(cudaMemcpyAsync(taps->weight_coarse + off * kNC, ws.weight, sizeof(float) * R * kNC, cudaMemcpyDeviceToDevice, st));
+    if (taps->srdf_coarse) UFO_CUDA(cudaMemcpyAsync(taps->srdf_coarse + off * kNC, ws.srdf, sizeof(float) * R * kNC, cudaMemcpyDeviceToDevice, st));
+  }
+  UFO_KERNEL("k_importance", st, k_importance<<<cdiv(R, 8), 256, 0, st>>>(ws.weight, ws.z_c, u_f + off, u_stride, R, ws.z_fine, ws.z_all));
+  const long long po = off * kNS;
+  float* pts = out->points ? out->points + off * kNS * 3 : nullptr;
+  float* sim8_tap = (taps && taps->sim8) ? taps->sim8 + po * 8 : nullptr;
+  float* ray_tap = (taps && taps->ray_out) ? taps->ray_out + po * kDRay : nullptr;
+  e = tc_pass(bf16, sc, w, R, kNS, ws.z_all, sim8_tap, pts, ray_tap, sms, st);
+  if (e) return e;
+  UFO_KERNEL("k_render<kNS>", st, k_render<kNS><<<cdiv(R, 8), 256, 0, st>>>(ws.z_all, ws.srdf, ws.radiance, w->inv_s, R, ws.weight,
+                                          out->depth ? out->depth + off : nullptr, out->rgb ? out->rgb + off * 3 : nullptr,
+                                          out->depth_z ? out->depth_z + off : nullptr, ws.rayinfo));
+  const long long P = (long long)R * kNS;
+  if (out->srdf) UFO_CUDA(cudaMemcpyAsync(out->srdf + off * kNS, ws.srdf, sizeof(float) * P, cudaMemcpyDeviceToDevice, st));
+  if (out->z) UFO_CUDA(cudaMemcpyAsync(out->z + off * kNS, ws.z_all, sizeof(float) * P, cudaMemcpyDeviceToDevice, st));
+  if (taps) {
+    if (taps->z_fine) UFO_CUDA(cudaMemcpyAsync(taps->z_fine + off * kNC, ws.z_fine, sizeof(float) * R * kNC, cudaMemcpyDeviceToDevice, st));
+    if (taps->tokens || taps->vol24) {
+      float* tk = taps->tokens ? taps->tokens + po * nv * kDView : nullptr;
+      float* vl = taps->vol24 ? taps->vol24 + po * 24 : nullptr;
+      if (bf16) UFO_KERNEL("k_tok_to_f32", st, k_tok_to_f32<true><<<cdiv(P * nv * kDView, 256), 256, 0, st>>>(ws.tok, nv, P, tk, vl));
+      else UFO_KERNEL("k_tok_to_f32", st, k_tok_to_f32<false><<<cdiv(P * nv * kDView, 256), 256, 0, st>>>(ws.tok, nv, P, tk, vl));
+    }
+    if (taps->view_tok0) UFO_CUDA(cudaMemcpyAsync(taps->view_tok0 + po * kDView, ws.vout0, sizeof(float) * P * kDView, cudaMemcpyDeviceToDevice, st));
+    if (taps->radiance && (e = copy_rows(reinterpret_cast<const float*>(ws.radiance), 4, taps->radiance + po * 3, 3, 3, P, st))) return e;
+    if (taps->weight) UFO_CUDA(cudaMemcpyAsync(taps->weight + po, ws.weight, sizeof(float) * P, cudaMemcpyDeviceToDevice, st));
+  }
+  return UFO_OK;
+}
+
 extern "C" int ufo_render_rays(const UfoScene* sc, const UfoWeights* w, const int64_t* ray_idx, int64_t ray_begin,
                                int32_t n_rays, const float* u_coarse, const float* u_fine, int64_t u_stride, int32_t mode,
                                const UfoRenderOut* out, const UfoDebugTaps* taps, void* stream_) {
   if (!sc || !w || !out || !u_coarse || !u_fine) return fail(UFO_EINVAL, "ufo_render_rays: null argument");
   if (n_rays < 0 || u_stride < n_rays) return fail(UFO_EINVAL, "ufo_render_rays: bad n_rays/u_stride");
-  if (mode != UFO_MODE_FP32 && mode != UFO_MODE_TC) return fail(UFO_EINVAL, "ufo_render_rays: unknown mode %d", mode);
+  if (mode != UFO_MODE_FP32 && mode != UFO_MODE_TC && mode != UFO_MODE_TC_F16) return fail(UFO_EINVAL, "ufo_render_rays: unknown mode %d", mode);
   if (!ray_idx && (ray_begin < 0 || ray_begin + n_rays > (int64_t)sc->d.H * sc->d.W))
     return fail(UFO_EINVAL, "ufo_render_rays: ray range [%lld,%lld) outside the %dx%d grid", (long long)ray_begin,
                 (long long)(ray_begin + n_rays), sc->d.H, sc->d.W);
@@ -501,8 +646,18 @@ extern "C" int ufo_render_rays(const UfoScene* sc, const UfoWeights* w, const in
   int sms = 0;
   UFO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   std::lock_guard<std::mutex> lock(sc->mu);
-  if (mode == UFO_MODE_TC)
-    return tc_render_rays(sc->d, w->tc, w->inv_s, ray_idx, ray_begin, n_rays, u_coarse, u_fine, u_stride, out, taps, sms, dev, st);
+  if (mode == UFO_MODE_TC || mode == UFO_MODE_TC_F16) {
+    int cc_major = 0;
+    UFO_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (cc_major != 10) return fail(UFO_ENODEVICE, "ufo_render_rays: the tensor-core modes need an sm_100 device (tcgen05), found sm_%d", cc_major * 10);
+    const int chunk = tc_chunk_rays(sms);
+    if (int e = tws_ensure(sc, n_rays < chunk ? n_rays : chunk)) return e;
+    for (int64_t off = 0; off < n_rays; off += chunk) {
+      const int R = (int)((n_rays - off) < chunk ? (n_rays - off) : chunk);
+      if (int e = render_chunk_tc(sc, w, mode == UFO_MODE_TC, ray_idx, ray_begin, R, u_coarse, u_fine, u_stride, off, out, taps, sms, st)) return e;
+    }
+    return UFO_OK;
+  }
   const int chunk = fp32_chunk_rays();
   if (int e = ws_ensure(sc, n_rays < chunk ? n_rays : chunk)) return e;
   for (int64_t off = 0; off < n_rays; off += chunk) {

@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(256) k_nchw_to_nhwc(const float* __restrict__ 
 }
 
 // (r,g,b) planes + MVS depth plane -> float4 texels.  imgs [N][3][S], depth [N][S] -> out [N][S].
-__global__ void __launch_bounds__(256) k_pack_rgbd(const float* __restrict__ imgs, const float* __restrict__ depth,
+static __global__ void __launch_bounds__(256) k_pack_rgbd(const float* __restrict__ imgs, const float* __restrict__ depth,
                                                   float4* __restrict__ out, long long S, int N) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= S * N) return;

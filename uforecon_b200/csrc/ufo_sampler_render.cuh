@@ -8,7 +8,7 @@
 namespace ufo {
 
 // rayinfo[r] = {d.x, d.y, d.z, cam_d.z, near, far, 0, 0}   (code1/model.py:409-427)
-__global__ void __launch_bounds__(256) k_ray_setup(SceneDev sc, const long long* __restrict__ ray_idx,
+static __global__ void __launch_bounds__(256) k_ray_setup(SceneDev sc, const long long* __restrict__ ray_idx,
                                                   long long ray_begin, int R, float* __restrict__ rayinfo) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R) return;
@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(256) k_ray_setup(SceneDev sc, const long long*
 }
 
 // z[r][i] = lin_i*(far-near)+near + (u-0.5)*(1/63)*(far-near);  u is [64][u_stride], column r.
-__global__ void __launch_bounds__(256) k_coarse_z(const float* __restrict__ rayinfo, const float* __restrict__ u,
+static __global__ void __launch_bounds__(256) k_coarse_z(const float* __restrict__ rayinfo, const float* __restrict__ u,
                                                  long long u_stride, int R, float* __restrict__ z) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)R * kNC) return;
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(256) k_render(const float* __restrict__ z, con
 }
 
 // Importance sampling + merge.  One warp per ray, 8 warps per block.
-__global__ void __launch_bounds__(256) k_importance(const float* __restrict__ weight, const float* __restrict__ zc,
+static __global__ void __launch_bounds__(256) k_importance(const float* __restrict__ weight, const float* __restrict__ zc,
                                                    const float* __restrict__ u, long long u_stride, int R,
                                                    float* __restrict__ z_fine_out, float* __restrict__ z_all) {
   __shared__ float s_cdf[8][kNC], s_zc[8][kNC], s_zf[8][kNC];

@@ -26,11 +26,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
       ".reg .pred P1;\n\t"
-      "WAIT_LOOP:\n\t"
+      "WAIT_LOOP_%=:\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-      "@P1 bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t"
+      "@P1 bra DONE_%=;\n\t"
+      "bra WAIT_LOOP_%=;\n\t"
+      "DONE_%=:\n\t"
       "}" ::"r"(smem_u32(bar)),
       "r"(parity)
       : "memory");

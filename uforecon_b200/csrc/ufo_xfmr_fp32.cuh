@@ -204,7 +204,7 @@ __device__ __forceinline__ void mlp3_eval(const Mlp3Dev& w, const float* __restr
 
 // pre_sim_mlp (8->32->32->16, ray_transformer.py:128-132,268) per point; writes the 16 values into
 // columns 56..71 of every view row of XV and the learnable view token into row 0 (:286-288).
-__global__ void __launch_bounds__(128) k_presim(const float* __restrict__ sim8, Mlp3Dev w,
+static __global__ void __launch_bounds__(128) k_presim(const float* __restrict__ sim8, Mlp3Dev w,
                                                const float* __restrict__ view_token, int L, long long P,
                                                float* __restrict__ XV) {
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(128) k_presim(const float* __restrict__ sim8, 
 }
 
 // Ray-stage input: [token-0 output of the view stage | sinusoid(sample index)] (ray_transformer.py:301-303)
-__global__ void __launch_bounds__(256) k_ray_tokens(const float* __restrict__ VOUT, int L, int SN, long long P,
+static __global__ void __launch_bounds__(256) k_ray_tokens(const float* __restrict__ VOUT, int L, int SN, long long P,
                                                    const float* __restrict__ pe_table /*[SN][8]*/,
                                                    float* __restrict__ XR /*[P][176]*/) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(256) k_ray_tokens(const float* __restrict__ VO
 }
 
 // DensityMLP 88->32->16->1 (ray_transformer.py:147-150,307)
-__global__ void __launch_bounds__(128) k_density(const float* __restrict__ ROUT, Mlp3Dev w, long long P,
+static __global__ void __launch_bounds__(128) k_density(const float* __restrict__ ROUT, Mlp3Dev w, long long P,
                                                 float* __restrict__ srdf) {
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(128) k_density(const float* __restrict__ ROUT,
 
 // Radiance blend: per view MLP 83->16->8->1 on [view feature | relative direction], masked softmax over
 // views, weighted colour (ray_transformer.py:310-320).
-__global__ void __launch_bounds__(128) k_radiance(const float* __restrict__ VOUT, const float4* __restrict__ dirs,
+static __global__ void __launch_bounds__(128) k_radiance(const float* __restrict__ VOUT, const float4* __restrict__ dirs,
                                                  const float4* __restrict__ rgbm, Mlp3Dev w, int NV, long long P,
                                                  float4* __restrict__ radiance) {
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
