@@ -254,7 +254,7 @@ def run_b200(args):
     weights = HotPathWeights(sd, dev)
     sc = Scene(batch, scene["source_imgs_feat"], scene["feature_volume"], scene["match_feature"], dev)
     H, W = sc.H, sc.W
-    n_rays = H * W
+    n_rays = H * W if args.rays <= 0 else min(args.rays, H * W)
     setup_s = time.time() - t0
 
     # sampler uniforms (FixedSampler / ImportanceSampler draws of the reference, sampler.py:42,86):
@@ -335,6 +335,8 @@ def run_b200(args):
     sharded_s = None
     begin, n_mine = ufodist.shard_rows(H, W, world, rank)
     counts = ufodist.shard_counts(H, W, world)
+    if args.rays > 0:
+        begin, n_mine, counts = 0, n_rays, [n_rays] * world
     for it in range(3):
         barrier()
         e0.record(stream)
@@ -439,6 +441,7 @@ def main():
     ap.add_argument("--cpu-chunks", type=int, default=4)
     ap.add_argument("--ref-chunks", type=int, default=2, help="--impl reference: 800-ray chunks per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rays", type=int, default=0, help="profiling aid: render only the first N rays of the map per step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

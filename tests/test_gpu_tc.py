@@ -1,0 +1,108 @@
+"""GPU: the tensor-core (tcgen05) modes of the hot path.
+
+Tolerances (BASELINE.json north_star): against the reference arithmetic on identical inputs the tensor-core
+transformer path must keep the p99 per-pixel depth error <= 0.5 % of the depth interval (the ray's sampled range
+far - near) and the rendered-colour PSNR >= 50 dB.  The isolated checks feed the oracle the CUDA
+path's own sample positions, so each bound is a statement about the 16-bit-operand kernels alone:
+bf16 operands carry 8 mantissa bits (2^-9 relative rounding), fp16 11 bits (2^-12).
+"""
+import math
+import os
+
+import pytest
+import torch
+
+from conftest import make_case, rel_err
+from oracle import uforecon_oracle as orc
+from uforecon_b200 import synthetic
+from uforecon_b200._lib import UFO_MODE_FP32, UFO_MODE_TC, UFO_MODE_TC_F16
+
+pytestmark = pytest.mark.gpu
+
+TAPS = ("z_coarse", "weight_coarse", "srdf_coarse", "z_fine", "sim8", "vol24", "tokens", "view_tok0", "ray_out", "radiance",
+        "weight")
+# per mode: (token rounding, view stage, ray stage, srdf) relative bounds = max|a-b| / max|ref|
+BOUNDS = {UFO_MODE_TC: (6e-3, 1.2e-2, 1.5e-2, 3e-2), UFO_MODE_TC_F16: (8e-4, 2e-3, 2e-3, 3e-3)}
+
+
+@pytest.fixture(scope="module", params=[3, 5])
+def tc_case(request):
+    from uforecon_b200.renderer import HotPathWeights, Scene, render_rays
+    nv = request.param
+    views = synthetic.UNFAVORABLE_VIEWS if nv == 3 else synthetic.TEN_VIEW_LIST[:nv]
+    wh = (160, 128)
+    batch, scene, sd = make_case(views, wh)
+    n = 301                                     # not a multiple of the tile sizes: exercises partial tiles
+    ray_idx = torch.randperm(wh[0] * wh[1], generator=torch.Generator().manual_seed(0))[:n]
+    u_c, u_f = synthetic.sampler_uniforms(n, seed=7)
+    w = HotPathWeights(sd)
+    sc = Scene(batch, scene["source_imgs_feat"], scene["feature_volume"], scene["match_feature"])
+    out = {}
+    for mode in (UFO_MODE_FP32, UFO_MODE_TC, UFO_MODE_TC_F16):
+        r = render_rays(sc, w, ray_idx, n, u_c, u_f, mode, want=("depth", "depth_z", "rgb", "srdf", "z", "points"), taps=TAPS)
+        torch.cuda.synchronize()
+        out[mode] = {k: v.cpu() for k, v in r.items()}
+    sc.close()
+    w.close()
+    return dict(batch=batch, scene=scene, sd=sd, ray_idx=ray_idx, n=n, nv=nv, out=out)
+
+
+@pytest.mark.parametrize("mode", [UFO_MODE_TC, UFO_MODE_TC_F16])
+def test_tc_kernels_isolated(tc_case, mode):
+    """gather (16-bit tokens) -> view stage -> ray stage -> SRDF head at the CUDA path's own sample positions."""
+    c = tc_case
+    r, batch, n, nv = c["out"][mode], c["batch"], c["n"], c["nv"]
+    z = r["z"]
+    d = batch["ray_d"][0][:, c["ray_idx"]].t()
+    pts = (batch["ray_o"][0][None, None] + z[:, :, None] * d[:, None, :]).float()
+    assert rel_err(r["points"], pts) <= 1e-6
+    with torch.no_grad():
+        o = orc.sample2rgb(batch, c["scene"], c["sd"], pts, z, detail=True)
+    b_tok, b_view, b_ray, b_srdf = BOUNDS[mode]
+    tok = o["tokens"].view(n, 128, nv, 80)
+    assert rel_err(r["sim8"], o["sim8"]) <= 1e-5                       # the similarity prior itself stays fp32
+    assert rel_err(r["tokens"][..., :72], tok[..., :72]) <= b_tok
+    assert float((r["tokens"][..., 72:] - tok[..., 72:]).abs().mean()) <= b_tok
+    vo = o["view_out"].view(n, 128, nv + 1, 80)[:, :, 0]
+    assert rel_err(r["view_tok0"], vo) <= b_view
+    assert rel_err(r["ray_out"], o["ray_out"]) <= b_ray
+    assert rel_err(r["srdf"], o["srdf"]) <= b_srdf
+    assert float((r["radiance"] - o["radiance"]).abs().mean()) <= 10 * b_tok / 6
+    # compositing downstream of the tensor-core stages is the same fp32 kernel: 1e-5 on its own inputs
+    rgb, depth, _, weight = orc.render(r["z"], r["radiance"], r["srdf"], c["sd"]["deviation_network.variance"])
+    assert rel_err(r["depth"], depth) <= 1e-5 and rel_err(r["rgb"], rgb) <= 1e-5 and rel_err(r["weight"], weight) <= 1e-5
+
+
+@pytest.mark.parametrize("mode", [UFO_MODE_TC, UFO_MODE_TC_F16])
+def test_tc_end_to_end_tolerance(tc_case, mode):
+    """north-star tolerance against the fp32 path (itself 1e-4 from the reference, test_gpu_parity.py)."""
+    c = tc_case
+    r, ref = c["out"][mode], c["out"][UFO_MODE_FP32]
+    span = float(c["batch"]["near_fars"][0, 0, 1] - c["batch"]["near_fars"][0, 0, 0])
+    de = (r["depth"] - ref["depth"]).abs() / span
+    assert float(de.quantile(0.99)) <= 5e-3, float(de.quantile(0.99))
+    mse = float(((r["rgb"] - ref["rgb"]) ** 2).mean())
+    assert 10 * math.log10(1.0 / max(mse, 1e-20)) >= 50.0
+
+
+def test_tc_chunking_invariance():
+    """rays are independent: the tiling of the tensor-core pipeline must not change any result bit."""
+    from uforecon_b200.renderer import HotPathWeights, Scene, render_rays
+    batch, scene, sd = make_case(synthetic.UNFAVORABLE_VIEWS, (96, 64))
+    n = 500
+    u_c, u_f = synthetic.sampler_uniforms(n, seed=5)
+    w = HotPathWeights(sd)
+    sc = Scene(batch, scene["source_imgs_feat"], scene["feature_volume"], scene["match_feature"])
+    full = render_rays(sc, w, None, n, u_c, u_f, UFO_MODE_TC, ray_begin=700)
+    os.environ["UFO_TC_CHUNK"] = "77"
+    try:
+        tiled = render_rays(sc, w, None, n, u_c, u_f, UFO_MODE_TC, ray_begin=700)
+    finally:
+        del os.environ["UFO_TC_CHUNK"]
+    part = render_rays(sc, w, None, 100, u_c[:, 100:200].contiguous(), u_f[:, 100:200].contiguous(), UFO_MODE_TC, ray_begin=800)
+    torch.cuda.synchronize()
+    for k in ("depth", "rgb", "depth_z"):
+        assert torch.equal(full[k], tiled[k]), k
+        assert torch.equal(full[k][100:200], part[k]), k
+    sc.close()
+    w.close()

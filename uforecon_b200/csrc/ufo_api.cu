@@ -552,7 +552,7 @@ static int tws_ensure(const UfoScene* sc, int rays) {
       {(void**)&w.rayinfo, (size_t)rays * 8 * 4}, {(void**)&w.z_c, (size_t)rays * kNC * 4}, {(void**)&w.z_all, P * 4},
       {(void**)&w.z_fine, (size_t)rays * kNC * 4}, {(void**)&w.vout0, P * kDView * 4}, {(void**)&w.srdf, P * 4},
       {(void**)&w.weight, P * 4}, {(void**)&w.tok, P * nv * kDView * 2}, {(void**)&w.rgbm, P * nv * 16},
-      {(void**)&w.dirs, P * nv * 16}, {(void**)&w.radiance, P * 16}};
+      {(void**)&w.dirs, P * nv * 16}, {(void**)&w.radiance, P * 16}, {(void**)&w.sim8, P * 8 * 4}, {(void**)&w.perm, P}};
   size_t total = 0;
   for (auto& it : items) total += (it.n + 255) & ~size_t(255);
   UFO_CUDA(cudaMalloc(&w.base, total));
@@ -563,25 +563,38 @@ static int tws_ensure(const UfoScene* sc, int rays) {
 }
 
 namespace ufo {
-int tc_pass(bool bf16, const UfoScene* sc, const UfoWeights* w, int R, int SN, const float* z, float* sim8_tap, float* pts,
-            float* ray_out_tap, int sms, cudaStream_t st) {
+int tc_pass(bool bf16, const UfoScene* sc, const UfoWeights* w, int R, int half, const float* z, bool want_sim8, float* ray_out_tap,
+            int sms, cudaStream_t st) {
   const bool lo = sc->d.nv <= 5;
-  if (bf16) return lo ? tc_pass_bf16_lo(sc, w, R, SN, z, sim8_tap, pts, ray_out_tap, sms, st) : tc_pass_bf16_hi(sc, w, R, SN, z, sim8_tap, pts, ray_out_tap, sms, st);
-  return lo ? tc_pass_f16_lo(sc, w, R, SN, z, sim8_tap, pts, ray_out_tap, sms, st) : tc_pass_f16_hi(sc, w, R, SN, z, sim8_tap, pts, ray_out_tap, sms, st);
+  if (bf16) return lo ? tc_pass_bf16_lo(sc, w, R, half, z, want_sim8, ray_out_tap, sms, st) : tc_pass_bf16_hi(sc, w, R, half, z, want_sim8, ray_out_tap, sms, st);
+  return lo ? tc_pass_f16_lo(sc, w, R, half, z, want_sim8, ray_out_tap, sms, st) : tc_pass_f16_hi(sc, w, R, half, z, want_sim8, ray_out_tap, sms, st);
 }
 }  // namespace ufo
 
-// debug taps of the 16-bit token rows: tokens [P][NV][80] and vol24 [P][24] as fp32
+// debug taps (sorted sample order) of the per-point buffers, which live in evaluation order [ray][128 slots]
 template <bool BF16>
-__global__ void k_tok_to_f32(const uint16_t* __restrict__ tok, int NV, long long P, float* __restrict__ tokens, float* __restrict__ vol24) {
+__global__ void k_tap_tokens(const uint16_t* __restrict__ tok, const uint8_t* __restrict__ perm, int NV, long long P,
+                             float* __restrict__ tokens, float* __restrict__ vol24) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= P * NV * kDView) return;
-  const uint32_t u = tok[t];
-  const float v = BF16 ? __uint_as_float(u << 16) : __half2float(__ushort_as_half((unsigned short)u));
-  if (tokens) tokens[t] = v;
   const int c = (int)(t % kDView);
   const long long pn = t / kDView;
-  if (vol24 && (pn % NV) == 0 && c >= 32 && c < 56) vol24[(pn / NV) * 24 + (c - 32)] = v;
+  const long long p = pn / NV;
+  const int n = (int)(pn % NV);
+  const long long src = (p / kNS) * kNS + perm[p];
+  const uint32_t u = tok[(src * NV + n) * kDView + c];
+  const float v = BF16 ? __uint_as_float(u << 16) : __half2float(__ushort_as_half((unsigned short)u));
+  if (tokens) tokens[t] = v;
+  if (vol24 && n == 0 && c >= 32 && c < 56) vol24[p * 24 + (c - 32)] = v;
+}
+
+__global__ void k_tap_rows(const float* __restrict__ src, int lds, const uint8_t* __restrict__ perm, int cols, long long P,
+                           float* __restrict__ dst) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= P * cols) return;
+  const long long p = t / cols;
+  const int c = (int)(t % cols);
+  dst[t] = src[((p / kNS) * kNS + perm[p]) * lds + c];
 }
 
 static int render_chunk_tc(const UfoScene* sc, const UfoWeights* w, bool bf16, const int64_t* ray_idx, int64_t ray_begin, int R,
@@ -590,27 +603,29 @@ static int render_chunk_tc(const UfoScene* sc, const UfoWeights* w, bool bf16, c
   const TcWorkspace& ws = sc->tws;
   const int nv = sc->d.nv;
   int e;
+  const bool want_sim8 = taps && taps->sim8;
   UFO_KERNEL("k_ray_setup", st, k_ray_setup<<<cdiv(R, 256), 256, 0, st>>>(sc->d, (const long long*)(ray_idx ? ray_idx + off : nullptr), ray_begin + off, R, ws.rayinfo));
   UFO_KERNEL("k_coarse_z", st, k_coarse_z<<<cdiv((long long)R * kNC, 256), 256, 0, st>>>(ws.rayinfo, u_c + off, u_stride, R, ws.z_c));
-  e = tc_pass(bf16, sc, w, R, kNC, ws.z_c, nullptr, nullptr, nullptr, sms, st);
-  if (e) return e;
-  UFO_KERNEL("k_render<kNC>", st, k_render<kNC><<<cdiv(R, 8), 256, 0, st>>>(ws.z_c, ws.srdf, ws.radiance, w->inv_s, R, ws.weight, nullptr, nullptr, nullptr, ws.rayinfo));
+  // coarse pass: 64 samples per ray -> slots 0..63
+  if ((e = tc_pass(bf16, sc, w, R, 0, ws.z_c, want_sim8, nullptr, sms, st))) return e;
+  UFO_KERNEL("k_render<kNC>", st, k_render<kNC><<<cdiv(R, 8), 256, 0, st>>>(ws.z_c, ws.srdf, ws.radiance, w->inv_s, R, ws.weight, nullptr, nullptr, nullptr,
+                                                                          ws.rayinfo, kNS, nullptr));
   if (taps) {
     if (taps->z_coarse) UFO_CUDA(cudaMemcpyAsync(taps->z_coarse + off * kNC, ws.z_c, sizeof(float) * R * kNC, cudaMemcpyDeviceToDevice, st));
     if (taps->weight_coarse) UFO_CUDA(cudaMemcpyAsync(taps->weight_coarse + off * kNC, ws.weight, sizeof(float) * R * kNC, cudaMemcpyDeviceToDevice, st));
     if (taps->srdf_coarse) UFO_CUDA(cudaMemcpyAsync(taps->srdf_coarse + off * kNC, ws.srdf, sizeof(float) * R * kNC, cudaMemcpyDeviceToDevice, st));
   }
-  UFO_KERNEL("k_importance", st, k_importance<<<cdiv(R, 8), 256, 0, st>>>(ws.weight, ws.z_c, u_f + off, u_stride, R, ws.z_fine, ws.z_all));
+  UFO_KERNEL("k_importance", st, k_importance<<<cdiv(R, 8), 256, 0, st>>>(ws.weight, ws.z_c, u_f + off, u_stride, R, ws.z_fine, ws.z_all, ws.perm));
+  // fine pass: only the 64 new samples go through the gathers and the view stage (slots 64..127); the ray stage
+  // runs over all 128 samples in sorted order
   const long long po = off * kNS;
-  float* pts = out->points ? out->points + off * kNS * 3 : nullptr;
-  float* sim8_tap = (taps && taps->sim8) ? taps->sim8 + po * 8 : nullptr;
+  const long long P = (long long)R * kNS;
   float* ray_tap = (taps && taps->ray_out) ? taps->ray_out + po * kDRay : nullptr;
-  e = tc_pass(bf16, sc, w, R, kNS, ws.z_all, sim8_tap, pts, ray_tap, sms, st);
-  if (e) return e;
+  if ((e = tc_pass(bf16, sc, w, R, 1, ws.z_fine, want_sim8, ray_tap, sms, st))) return e;
   UFO_KERNEL("k_render<kNS>", st, k_render<kNS><<<cdiv(R, 8), 256, 0, st>>>(ws.z_all, ws.srdf, ws.radiance, w->inv_s, R, ws.weight,
                                           out->depth ? out->depth + off : nullptr, out->rgb ? out->rgb + off * 3 : nullptr,
-                                          out->depth_z ? out->depth_z + off : nullptr, ws.rayinfo));
-  const long long P = (long long)R * kNS;
+                                          out->depth_z ? out->depth_z + off : nullptr, ws.rayinfo, kNS, ws.perm));
+  if (out->points) UFO_KERNEL("k_points", st, k_points<<<cdiv(P, 256), 256, 0, st>>>(sc->d, ws.rayinfo, ws.z_all, P, kNS, out->points + po * 3));
   if (out->srdf) UFO_CUDA(cudaMemcpyAsync(out->srdf + off * kNS, ws.srdf, sizeof(float) * P, cudaMemcpyDeviceToDevice, st));
   if (out->z) UFO_CUDA(cudaMemcpyAsync(out->z + off * kNS, ws.z_all, sizeof(float) * P, cudaMemcpyDeviceToDevice, st));
   if (taps) {
@@ -618,11 +633,12 @@ static int render_chunk_tc(const UfoScene* sc, const UfoWeights* w, bool bf16, c
     if (taps->tokens || taps->vol24) {
       float* tk = taps->tokens ? taps->tokens + po * nv * kDView : nullptr;
       float* vl = taps->vol24 ? taps->vol24 + po * 24 : nullptr;
-      if (bf16) UFO_KERNEL("k_tok_to_f32", st, k_tok_to_f32<true><<<cdiv(P * nv * kDView, 256), 256, 0, st>>>(ws.tok, nv, P, tk, vl));
-      else UFO_KERNEL("k_tok_to_f32", st, k_tok_to_f32<false><<<cdiv(P * nv * kDView, 256), 256, 0, st>>>(ws.tok, nv, P, tk, vl));
+      if (bf16) UFO_KERNEL("k_tap_tokens", st, k_tap_tokens<true><<<cdiv(P * nv * kDView, 256), 256, 0, st>>>(ws.tok, ws.perm, nv, P, tk, vl));
+      else UFO_KERNEL("k_tap_tokens", st, k_tap_tokens<false><<<cdiv(P * nv * kDView, 256), 256, 0, st>>>(ws.tok, ws.perm, nv, P, tk, vl));
     }
-    if (taps->view_tok0) UFO_CUDA(cudaMemcpyAsync(taps->view_tok0 + po * kDView, ws.vout0, sizeof(float) * P * kDView, cudaMemcpyDeviceToDevice, st));
-    if (taps->radiance && (e = copy_rows(reinterpret_cast<const float*>(ws.radiance), 4, taps->radiance + po * 3, 3, 3, P, st))) return e;
+    if (taps->sim8) UFO_KERNEL("k_tap_rows", st, k_tap_rows<<<cdiv(P * 8, 256), 256, 0, st>>>(ws.sim8, 8, ws.perm, 8, P, taps->sim8 + po * 8));
+    if (taps->view_tok0) UFO_KERNEL("k_tap_rows", st, k_tap_rows<<<cdiv(P * kDView, 256), 256, 0, st>>>(ws.vout0, kDView, ws.perm, kDView, P, taps->view_tok0 + po * kDView));
+    if (taps->radiance) UFO_KERNEL("k_tap_rows", st, k_tap_rows<<<cdiv(P * 3, 256), 256, 0, st>>>(reinterpret_cast<const float*>(ws.radiance), 4, ws.perm, 3, P, taps->radiance + po * 3));
     if (taps->weight) UFO_CUDA(cudaMemcpyAsync(taps->weight + po, ws.weight, sizeof(float) * P, cudaMemcpyDeviceToDevice, st));
   }
   return UFO_OK;

@@ -33,8 +33,9 @@ struct TcWorkspace {
   uint8_t* base = nullptr;
   size_t bytes = 0;
   int cap_rays = 0, nv = 0;
-  float *rayinfo, *z_c, *z_all, *z_fine, *vout0, *srdf, *weight;
+  float *rayinfo, *z_c, *z_all, *z_fine, *vout0, *srdf, *weight, *sim8;
   uint16_t* tok;
+  uint8_t* perm;    // [rays][128] evaluation-order index of each sorted sample (k_importance)
   float4 *rgbm, *dirs, *radiance;
 };
 
@@ -64,10 +65,10 @@ struct UfoScene {
 namespace ufo {
 // One sample2rgb pass of the tensor-core pipeline (gather -> view stage -> ray stage); defined per operand
 // format and view-count group in ufo_tc_inst_*.cu.
-int tc_pass(bool bf16, const UfoScene* sc, const UfoWeights* w, int R, int SN, const float* z, float* sim8_tap, float* pts,
+int tc_pass(bool bf16, const UfoScene* sc, const UfoWeights* w, int R, int half, const float* z, bool want_sim8,
             float* ray_out_tap, int sms, cudaStream_t st);
-int tc_pass_bf16_lo(const UfoScene*, const UfoWeights*, int, int, const float*, float*, float*, float*, int, cudaStream_t);
-int tc_pass_bf16_hi(const UfoScene*, const UfoWeights*, int, int, const float*, float*, float*, float*, int, cudaStream_t);
-int tc_pass_f16_lo(const UfoScene*, const UfoWeights*, int, int, const float*, float*, float*, float*, int, cudaStream_t);
-int tc_pass_f16_hi(const UfoScene*, const UfoWeights*, int, int, const float*, float*, float*, float*, int, cudaStream_t);
+int tc_pass_bf16_lo(const UfoScene*, const UfoWeights*, int, int, const float*, bool, float*, int, cudaStream_t);
+int tc_pass_bf16_hi(const UfoScene*, const UfoWeights*, int, int, const float*, bool, float*, int, cudaStream_t);
+int tc_pass_f16_lo(const UfoScene*, const UfoWeights*, int, int, const float*, bool, float*, int, cudaStream_t);
+int tc_pass_f16_hi(const UfoScene*, const UfoWeights*, int, int, const float*, bool, float*, int, cudaStream_t);
 }  // namespace ufo

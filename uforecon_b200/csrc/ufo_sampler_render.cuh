@@ -55,7 +55,10 @@ __global__ void __launch_bounds__(256) k_render(const float* __restrict__ z, con
                                                const float4* __restrict__ radiance, float inv_s, int R,
                                                float* __restrict__ weight_out, float* __restrict__ depth_out,
                                                float* __restrict__ rgb_out, float* __restrict__ depthz_out,
-                                               const float* __restrict__ rayinfo) {
+                                               const float* __restrict__ rayinfo, int rad_stride = SN,
+                                               const uint8_t* __restrict__ perm = nullptr) {
+  // radiance of sample i of ray r is radiance[r*rad_stride + (perm ? perm[r*SN+i] : i)]  (the tensor-core path keeps
+  // per-point results in evaluation order: 64 coarse then 64 importance samples, see k_importance)
   constexpr int K = SN / 32;
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= R) return;
@@ -97,7 +100,7 @@ __global__ void __launch_bounds__(256) k_render(const float* __restrict__ z, con
     const float w = alpha[k] * T;
     T *= (1.f - alpha[k]) + 1e-7f;
     if (weight_out) weight_out[(size_t)r * SN + i] = w;
-    const float4 c = radiance[(size_t)r * SN + i];
+    const float4 c = radiance[(size_t)r * rad_stride + (perm ? (int)perm[(size_t)r * SN + i] : i)];
     acc_r = fmaf(c.x, w, acc_r);
     acc_g = fmaf(c.y, w, acc_g);
     acc_b = fmaf(c.z, w, acc_b);
@@ -122,7 +125,10 @@ __global__ void __launch_bounds__(256) k_render(const float* __restrict__ z, con
 // Importance sampling + merge.  One warp per ray, 8 warps per block.
 static __global__ void __launch_bounds__(256) k_importance(const float* __restrict__ weight, const float* __restrict__ zc,
                                                    const float* __restrict__ u, long long u_stride, int R,
-                                                   float* __restrict__ z_fine_out, float* __restrict__ z_all) {
+                                                   float* __restrict__ z_fine_out, float* __restrict__ z_all,
+                                                   uint8_t* __restrict__ perm = nullptr) {
+  // perm [R][128] (optional): evaluation-order index of the sample at each sorted position
+  // (0..63 = coarse sample i, 64..127 = importance sample i of the sorted fine list)
   __shared__ float s_cdf[8][kNC], s_zc[8][kNC], s_zf[8][kNC];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + wid;
@@ -188,15 +194,29 @@ static __global__ void __launch_bounds__(256) k_importance(const float* __restri
       int lo = 0, hi = kNC;
       while (lo < hi) { const int mid = (lo + hi) >> 1; if (zf[mid] < val) lo = mid + 1; else hi = mid; }
       out[i + lo] = val;
+      if (perm) perm[(size_t)r * kNS + i + lo] = (uint8_t)i;
     }
     {  // fine element i: count coarse <= zf
       const float val = zf[i];
       int lo = 0, hi = kNC;
       while (lo < hi) { const int mid = (lo + hi) >> 1; if (zcs[mid] <= val) lo = mid + 1; else hi = mid; }
       out[i + lo] = val;
+      if (perm) perm[(size_t)r * kNS + i + lo] = (uint8_t)(kNC + i);
     }
     if (z_fine_out) z_fine_out[(size_t)r * kNC + i] = zf[i];
   }
+}
+
+// points_x_all of infer (model.py:466-470): x = o + z d for the merged, sorted samples
+static __global__ void __launch_bounds__(256) k_points(SceneDev sc, const float* __restrict__ rayinfo, const float* __restrict__ z,
+                                                       long long n, int SN, float* __restrict__ pts) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const float* ri = rayinfo + (size_t)(p / SN) * 8;
+  const float zz = z[p];
+  pts[p * 3 + 0] = __fadd_rn(sc.ray_o[0], __fmul_rn(zz, ri[0]));
+  pts[p * 3 + 1] = __fadd_rn(sc.ray_o[1], __fmul_rn(zz, ri[1]));
+  pts[p * 3 + 2] = __fadd_rn(sc.ray_o[2], __fmul_rn(zz, ri[2]));
 }
 
 }  // namespace ufo

@@ -5,14 +5,17 @@
 #include "ufo_xfmr_tc.cuh"
 
 namespace ufo {
+// One sample2rgb pass of the tensor-core pipeline over the R*64 points of half `half` (0: coarse samples,
+// 1: importance samples): gather -> view stage, then the ray stage over the 64 coarse samples (half 0) or over
+// all 128 samples in sorted order through ws.perm (half 1).
 template <int NV, bool BF16>
-static int launch_tc_pass(const UfoScene* sc, const UfoWeights* w, int R, int SN, const float* z, float* sim8_tap, float* pts,
+static int launch_tc_pass(const UfoScene* sc, const UfoWeights* w, int R, int half, const float* z, bool want_sim8,
                           float* ray_out_tap, int sms, cudaStream_t st) {
   const TcWorkspace& ws = sc->tws;
-  const long long P = (long long)R * SN;
+  const long long P = (long long)R * kNC;
   const int f = BF16 ? 0 : 1;
-  UFO_KERNEL("k_gather_tc", st, k_gather_tc<NV, BF16><<<cdiv(P, 256), 256, 0, st>>>(sc->d, ws.rayinfo, z, R, SN, w->freqs, w->phases, w->pre_sim,
-                                                                                  ws.tok, ws.rgbm, ws.dirs, sim8_tap, pts));
+  UFO_KERNEL("k_gather_tc", st, k_gather_tc<NV, BF16><<<cdiv(P, 256), 256, 0, st>>>(sc->d, ws.rayinfo, z, R, half, w->freqs, w->phases, w->pre_sim,
+                                                                                  ws.tok, ws.rgbm, ws.dirs, want_sim8 ? ws.sim8 : nullptr));
   {
     static bool attr = false;
     if (!attr) {
@@ -22,32 +25,31 @@ static int launch_tc_pass(const UfoScene* sc, const UfoWeights* w, int R, int SN
     constexpr int PPT = 128 / (NV + 1);
     const long long tiles = (P + PPT - 1) / PPT;
     const int grid = (int)(tiles < sms ? tiles : sms);
-    UFO_KERNEL("k_view_tc", st, k_view_tc<NV, BF16><<<grid, tc::kThreads, tc::V_SMEM, st>>>(w->tc.view_img[f], w->tc.vp, ws.tok, ws.rgbm, ws.dirs, P,
+    UFO_KERNEL("k_view_tc", st, k_view_tc<NV, BF16><<<grid, tc::kThreads, tc::V_SMEM, st>>>(w->tc.view_img[f], w->tc.vp, ws.tok, ws.rgbm, ws.dirs, P, half,
                                                                                            ws.vout0, ws.radiance));
   }
-  {
+  if (half == 0) {
     const long long tiles = (P + 127) / 128;
     const int grid = (int)(tiles < sms ? tiles : sms);
-    if (SN == kNC) {
-      static bool attr = false;
-      if (!attr) { UFO_CUDA(cudaFuncSetAttribute(k_ray_tc<kNC, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::R_SMEM)); attr = true; }
-      UFO_KERNEL("k_ray_tc", st, k_ray_tc<kNC, BF16><<<grid, tc::kThreads, tc::R_SMEM, st>>>(w->tc.ray_img[f], w->tc.rp, ws.vout0, w->pe_table, P, ws.srdf, ray_out_tap));
-    } else {
-      static bool attr = false;
-      if (!attr) { UFO_CUDA(cudaFuncSetAttribute(k_ray_tc<kNS, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::R_SMEM)); attr = true; }
-      UFO_KERNEL("k_ray_tc", st, k_ray_tc<kNS, BF16><<<grid, tc::kThreads, tc::R_SMEM, st>>>(w->tc.ray_img[f], w->tc.rp, ws.vout0, w->pe_table, P, ws.srdf, ray_out_tap));
-    }
+    static bool attr = false;
+    if (!attr) { UFO_CUDA(cudaFuncSetAttribute(k_ray_tc<kNC, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::R_SMEM)); attr = true; }
+    UFO_KERNEL("k_ray_tc", st, k_ray_tc<kNC, BF16><<<grid, tc::kThreads, tc::R_SMEM, st>>>(w->tc.ray_img[f], w->tc.rp, ws.vout0, w->pe_table, nullptr, P, ws.srdf, ray_out_tap));
+  } else {
+    const long long tiles = R;
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    static bool attr = false;
+    if (!attr) { UFO_CUDA(cudaFuncSetAttribute(k_ray_tc<kNS, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::R_SMEM)); attr = true; }
+    UFO_KERNEL("k_ray_tc", st, k_ray_tc<kNS, BF16><<<grid, tc::kThreads, tc::R_SMEM, st>>>(w->tc.ray_img[f], w->tc.rp, ws.vout0, w->pe_table, ws.perm, (long long)R * kNS, ws.srdf, ray_out_tap));
   }
   return UFO_OK;
 }
 
-
 #define UFO_TC_DEFINE_PASS(fn, BF16, ...)                                                                                   \
-  int fn(const UfoScene* sc, const UfoWeights* w, int R, int SN, const float* z, float* sim8_tap, float* pts,              \
+  int fn(const UfoScene* sc, const UfoWeights* w, int R, int half, const float* z, bool want_sim8,                          \
          float* ray_out_tap, int sms, cudaStream_t st) {                                                                     \
     switch (sc->d.nv) { __VA_ARGS__ }                                                                                        \
     return fail(UFO_EINVAL, "unsupported n_views");                                                                          \
   }
 #define UFO_TC_CASE(NV, BF16) \
-  case NV: return launch_tc_pass<NV, BF16>(sc, w, R, SN, z, sim8_tap, pts, ray_out_tap, sms, st);
+  case NV: return launch_tc_pass<NV, BF16>(sc, w, R, half, z, want_sim8, ray_out_tap, sms, st);
 }  // namespace ufo

@@ -103,13 +103,19 @@ __device__ __forceinline__ void issue_gemm_sub(uint32_t tmem_d, uint32_t a_base,
 // view-stage kernel loads, pre_sim_mlp (ray_transformer.py:128-132,268) fused in.
 // tok [P][NV][80] 16-bit: [feat 32 | vol 24 | sim 16 | depth-PE 8]
 // =================================================================================================
+// Per-point buffers of the tensor-core path are laid out [ray][128 slots]: slots 0..63 hold the coarse samples,
+// 64..127 the importance samples, both in evaluation order, so that the fine pass of infer only evaluates the 64
+// NEW points of a ray (the view stage is point-wise: re-evaluating the coarse points, as the reference does, gives
+// identical values).  A pass over R*64 points with half = 0 | 1 addresses slot(p).
+__device__ __forceinline__ long long tc_slot(long long p, int half) { return (p >> 6) * kNS + half * kNC + (p & 63); }
+
 template <int NV, bool BF16>
 __global__ void __launch_bounds__(256) k_gather_tc(SceneDev sc, const float* __restrict__ rayinfo,
-                                                   const float* __restrict__ zbuf, int R, int SN,
+                                                   const float* __restrict__ zbuf, int R, int half,
                                                    const float* __restrict__ freqs, const float* __restrict__ phases,
                                                    Mlp3Dev presim, uint16_t* __restrict__ tok, float4* __restrict__ rgbm,
-                                                   float4* __restrict__ dirs, float* __restrict__ sim8_out,
-                                                   float* __restrict__ pts_out) {
+                                                   float4* __restrict__ dirs, float* __restrict__ sim8_out) {
+  constexpr int SN = kNC;
   __shared__ float s_sim[256][9];
   __shared__ float s_w[8 * 32 + 32 + 32 * 32 + 32 + 32 * 16 + 16];
   {  // pre_sim_mlp weights -> shared memory
@@ -136,9 +142,10 @@ __global__ void __launch_bounds__(256) k_gather_tc(SceneDev sc, const float* __r
     const float z = __fadd_rn(sc.ray_o[2], __fmul_rn(zz, ri[2]));
     PointGather<NV> g;
     gather_point<NV>(sc, x, y, z, j, fj, pj, g);
+    const size_t sl = (size_t)tc_slot(p, half);
 #pragma unroll
     for (int n = 0; n < NV; ++n) {
-      uint16_t* row = tok + ((size_t)p * NV + n) * kDView;
+      uint16_t* row = tok + (sl * NV + n) * kDView;
       uint2 f;
       f.x = umma::pack2<BF16>(g.feat[n].x, g.feat[n].y);
       f.y = umma::pack2<BF16>(g.feat[n].z, g.feat[n].w);
@@ -148,13 +155,12 @@ __global__ void __launch_bounds__(256) k_gather_tc(SceneDev sc, const float* __r
       row[48 + j] = (uint16_t)(umma::pack2<BF16>(g.vol[2], 0.f) & 0xffffu);
       row[72 + j] = (uint16_t)(umma::pack2<BF16>(g.pe[n], 0.f) & 0xffffu);
       if (j == 0) {
-        rgbm[(size_t)p * NV + n] = g.rgbm[n];
-        dirs[(size_t)p * NV + n] = g.dir[n];
+        rgbm[sl * NV + n] = g.rgbm[n];
+        dirs[sl * NV + n] = g.dir[n];
       }
     }
     s_sim[round * 32 + sub][j] = g.sim;
-    if (sim8_out != nullptr) sim8_out[(size_t)p * 8 + j] = g.sim;
-    if (pts_out != nullptr && j < 3) pts_out[(size_t)p * 3 + j] = (j == 0) ? x : (j == 1 ? y : z);
+    if (sim8_out != nullptr) sim8_out[sl * 8 + j] = g.sim;
   }
   __syncthreads();
   const long long p = p0 + threadIdx.x;
@@ -194,9 +200,10 @@ __global__ void __launch_bounds__(256) k_gather_tc(SceneDev sc, const float* __r
     o16[o] = a;
   }
   const uint4 lo = tc::pack8<BF16>(o16), hi = tc::pack8<BF16>(o16 + 8);
+  const size_t sl = (size_t)tc_slot(p, half);
 #pragma unroll
   for (int n = 0; n < NV; ++n) {
-    uint16_t* row = tok + ((size_t)p * NV + n) * kDView;
+    uint16_t* row = tok + (sl * NV + n) * kDView;
     *reinterpret_cast<uint4*>(row + 56) = lo;
     *reinterpret_cast<uint4*>(row + 64) = hi;
   }
@@ -208,8 +215,8 @@ __global__ void __launch_bounds__(256) k_gather_tc(SceneDev sc, const float* __r
 template <int NV, bool BF16>
 __global__ void __launch_bounds__(tc::kThreads, 1)
 k_view_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams prm, const uint16_t* __restrict__ tok,
-          const float4* __restrict__ rgbm, const float4* __restrict__ dirs, long long P, float* __restrict__ vout0,
-          float4* __restrict__ radiance) {
+          const float4* __restrict__ rgbm, const float4* __restrict__ dirs, long long P, int half,
+          float* __restrict__ vout0, float4* __restrict__ radiance) {
   using namespace tc;
   constexpr int L = NV + 1, PPT = 128 / L, ROWS = PPT * L;
   constexpr uint32_t FMT = BF16 ? umma::kFmtBF16 : umma::kFmtF16;
@@ -258,17 +265,18 @@ k_view_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams p
       if (rr < ROWS && ll > 0) {
         const long long p = pbase + pr;
         uint4 v = make_uint4(0, 0, 0, 0);
-        if (p < P) v = __ldg(reinterpret_cast<const uint4*>(tok + ((size_t)p * NV + (ll - 1)) * kDView) + c);
+        if (p < P) v = __ldg(reinterpret_cast<const uint4*>(tok + ((size_t)tc_slot(p, half) * NV + (ll - 1)) * kDView) + c);
         *reinterpret_cast<uint4*>(tile_ptr(smem + V_X, rr, c)) = v;
       }
     }
     const long long my_p = pbase + pl;
+    const size_t my_slot = (size_t)tc_slot(my_p, half);
     const bool view_row = row_ok && l > 0 && my_p < P;
     float4 my_dir = make_float4(0.f, 0.f, 0.f, 0.f);
     float my_mask = 0.f;
     if (g == 0 && view_row) {
-      my_dir = __ldg(dirs + (size_t)my_p * NV + (l - 1));
-      my_mask = __ldg(rgbm + (size_t)my_p * NV + (l - 1)).w;
+      my_dir = __ldg(dirs + my_slot * NV + (l - 1));
+      my_mask = __ldg(rgbm + my_slot * NV + (l - 1)).w;
     }
     umma::fence_async_smem();
     umma::tc_fence_before();
@@ -487,7 +495,7 @@ k_view_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams p
           for (int k = 0; k < 8; ++k) o[k] = (v[8 * i + k] - mean) * rstd * prm.n2w[8 * c + k] + prm.n2b[8 * c + k];
           st_chunk<BF16>(smem + V_M, r, c, o);
           if (row_ok && l == 0 && my_p < P) {
-            float4* dst = reinterpret_cast<float4*>(vout0 + (size_t)my_p * kDView + 8 * c);
+            float4* dst = reinterpret_cast<float4*>(vout0 + my_slot * kDView + 8 * c);
             dst[0] = make_float4(prm.vtok[8 * c] + o[0], prm.vtok[8 * c + 1] + o[1], prm.vtok[8 * c + 2] + o[2], prm.vtok[8 * c + 3] + o[3]);
             dst[1] = make_float4(prm.vtok[8 * c + 4] + o[4], prm.vtok[8 * c + 5] + o[5], prm.vtok[8 * c + 6] + o[6], prm.vtok[8 * c + 7] + o[7]);
           }
@@ -531,7 +539,7 @@ k_view_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams p
     umma::tc_fence_before();
     __syncthreads();
     if (tid < PPT && pbase + tid < P) {
-      const long long p = pbase + tid;
+      const size_t p = (size_t)tc_slot(pbase + tid, half);
       float om[NV];
       float mx = -INFINITY;
 #pragma unroll
@@ -548,7 +556,7 @@ k_view_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams p
       float cr = 0.f, cg = 0.f, cb = 0.f;
 #pragma unroll
       for (int n = 0; n < NV; ++n) {
-        const float4 c = __ldg(rgbm + (size_t)p * NV + n);
+        const float4 c = __ldg(rgbm + p * NV + n);
         const float pw = om[n] / den;
         cr = fmaf(c.x, pw, cr);
         cg = fmaf(c.y, pw, cg);
@@ -572,7 +580,8 @@ k_view_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams p
 template <int SN, bool BF16>
 __global__ void __launch_bounds__(tc::kThreads, 1)
 k_ray_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams prm, const float* __restrict__ vout0,
-         const float* __restrict__ pe_table, long long P, float* __restrict__ srdf, float* __restrict__ ray_out) {
+         const float* __restrict__ pe_table, const uint8_t* __restrict__ perm, long long P, float* __restrict__ srdf,
+         float* __restrict__ ray_out) {
   using namespace tc;
   constexpr uint32_t FMT = BF16 ? umma::kFmtBF16 : umma::kFmtF16;
   constexpr int NSEQ = 128 / SN;
@@ -623,8 +632,11 @@ k_ray_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams prm
   constexpr uint32_t D_QKV = 0, D_KV = 272, D_MSG = 0, D_MRG = 96, D_ML0 = 192, D_ML2 = 0, D_DEN = 96;
 
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long prow = tile * 128 + r;           // this thread's token (global point index)
+    const long long prow = tile * 128 + r;           // this thread's token: ray prow/SN, sorted sample prow%SN
     const bool row_ok = prow < P;
+    // its view-stage result lives at slot(ray, evaluation index): coarse pass = sample index, fine pass = perm
+    size_t in_row = 0;
+    if (row_ok) in_row = (SN == kNC) ? (size_t)tc_slot(prow, 0) : (size_t)(tile * 128 + (perm ? (int)perm[prow] : r));
     // ---- R0: x = token-0 output of the view stage -> 16-bit A operand (columns 80..87 = order PE, constant)
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -632,8 +644,8 @@ k_ray_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams prm
       if (c < 10) {
         float v[8];
         if (row_ok) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(vout0 + (size_t)prow * kDView + 8 * c));
-          const float4 b = __ldg(reinterpret_cast<const float4*>(vout0 + (size_t)prow * kDView + 8 * c + 4));
+          const float4 a = __ldg(reinterpret_cast<const float4*>(vout0 + in_row * kDView + 8 * c));
+          const float4 b = __ldg(reinterpret_cast<const float4*>(vout0 + in_row * kDView + 8 * c + 4));
           v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
         } else {
   #pragma unroll
@@ -897,8 +909,8 @@ k_ray_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams prm
             float x[8];
             if (c < 10) {
               if (row_ok) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(vout0 + (size_t)prow * kDView + 8 * c));
-                const float4 b = __ldg(reinterpret_cast<const float4*>(vout0 + (size_t)prow * kDView + 8 * c + 4));
+                const float4 a = __ldg(reinterpret_cast<const float4*>(vout0 + in_row * kDView + 8 * c));
+                const float4 b = __ldg(reinterpret_cast<const float4*>(vout0 + in_row * kDView + 8 * c + 4));
                 x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
               } else {
   #pragma unroll
