@@ -157,9 +157,12 @@ def test_end_to_end_fp32_vs_oracle_and_golden(case):
         assert rel_err(r["rgb"][clean], torch.as_tensor(ref["rgb"])[clean]) <= 1e-4
         assert rel_err(r["z"], ref["z"]) <= 1e-4
         assert rel_err(r["srdf"], ref["srdf"]) <= 2e-4
+    # taps at the CUDA path's own fine samples vs the golden's: the sample positions agree to 1e-4 (asserted above)
+    # and the synthetic feature fields vary by O(1) over ~1e-1, so 2e-3 here; the kernels themselves are held to
+    # 1e-5 at identical positions in test_gather_kernels_isolated
     dr = case["dr"]
-    assert rel_err(r["sim8"][:dr], g["sim8_f"]) <= 1e-4
-    assert rel_err(r["vol24"][:dr], g["vol24_f"]) <= 1e-4
+    assert rel_err(r["sim8"][:dr], g["sim8_f"]) <= 2e-3
+    assert rel_err(r["vol24"][:dr], g["vol24_f"]) <= 2e-3
 
 
 def test_chunking_and_ray_range_invariance():

@@ -45,9 +45,18 @@ def main():
         rgb, depth, _, weight = orc.render(r["z"], r["radiance"], r["srdf"], sd["deviation_network.variance"])
         print("  compositing ", rel_err(r["depth"], depth), rel_err(r["rgb"], rgb))
         # end to end against the fp32 CUDA path (same uniforms)
+        import math
         de = (r["depth"] - ref["depth"].cpu()).abs() / span
         mse = float(((r["rgb"] - ref["rgb"].cpu()) ** 2).mean())
-        import math
+        amb = ((o["uv"].abs() - 1).abs() < 2e-5).any(-1).any(0).any(1)          # rays with a mask-ambiguous sample
+        with torch.no_grad():
+            o32 = orc.sample2rgb(batch, scene, sd, (batch["ray_o"][0][None, None] + ref["z"].cpu()[:, :, None] * d[:, None, :]).float(), ref["z"].cpu(), detail=True)
+        amb |= ((o32["uv"].abs() - 1).abs() < 2e-5).any(-1).any(0).any(1)
+        er = (r["rgb"] - ref["rgb"].cpu()).abs().max(1)[0]
+        top = er.argsort(descending=True)[:6]
+        print("  top rgb err", [(int(i), round(float(er[i]), 5), bool(amb[i]), round(float(de[i]), 6)) for i in top], "n_amb", int(amb.sum()))
+        mse_c = float(((r["rgb"] - ref["rgb"].cpu())[~amb] ** 2).mean())
+        print(f"  PSNR without ambiguous rays {10 * math.log10(1.0 / max(mse_c, 1e-20)):.1f} dB")
         print(f"  e2e depth err/interval: p50 {float(de.median()):.3e} p99 {float(de.quantile(0.99)):.3e} max {float(de.max()):.3e};"
               f" rgb PSNR {10 * math.log10(1.0 / max(mse, 1e-20)):.1f} dB")
     sc.close(); w.close()

@@ -71,7 +71,39 @@ def hot_path_layout() -> Dict[str, Tuple[int, ...]]:
     return lay
 
 
-def synthetic_state_dict(seed: int = 0, inv_s: float = 20.0) -> Dict[str, torch.Tensor]:
+def _shape_surface_head(sd: Dict[str, torch.Tensor], gen: torch.Generator) -> None:
+    """Make the random SRDF head behave like a trained one: positive in front of a surface, a single zero
+    crossing somewhere along the ray, negative behind, slope ~ -1 per unit of ray distance.
+
+    With purely random weights the SRDF is negative at the first sample of most rays, NeuS gives that sample
+    alpha = 1 and the rendered depth collapses onto ``near`` - a depth that does not depend on the network at all
+    would make every depth tolerance in the tests vacuous.  The construction uses the one input the head sees
+    un-mixed: the sample-order encoding ``sin(i/1000)`` that ``RayTransformer`` concatenates to the ray tokens
+    (ray_transformer.py:165-173, 301-303; column 86 of the residual stream), plus a small random projection of
+    the other features so that the crossing moves from ray to ray and the profile is not perfectly smooth.
+    """
+    rt = "ray_transformer."
+    # keep the residual stream's order-encoding columns (80..87) close to the encoding itself
+    sd[rt + "density_ray_transformer.layers.0.norm2.weight"][80:] *= 1e-3
+    sd[rt + "density_ray_transformer.layers.0.norm2.bias"][80:] = 0.0
+    w0, b0 = sd[rt + "DensityMLP.0.weight"], sd[rt + "DensityMLP.0.bias"]
+    w2, b2 = sd[rt + "DensityMLP.2.weight"], sd[rt + "DensityMLP.2.bias"]
+    w4, b4 = sd[rt + "DensityMLP.4.weight"], sd[rt + "DensityMLP.4.bias"]
+    alpha, c, beta, s0 = 20.0, 0.2, 0.905, 1.0
+    w0[0].zero_()
+    w0[0, :80] = (torch.rand(80, generator=gen) * 2 - 1) * (0.05 / math.sqrt(80.0 / 3.0))
+    w0[0, 86] = -alpha
+    b0[0] = alpha * c                       # h0 = 4 - 20 sin(i/1000) + noise   (always > 0)
+    w2[0].zero_()
+    w2[0, 0] = 1.0
+    b2[0] = 0.0                             # g0 = h0
+    w2[1:, 0] = 0.0                         # the other hidden units do not see the ramp
+    w4.mul_(0.1)
+    w4[0, 0] = beta                         # srdf = 0.905 g0 - 2.62 + small random part
+    b4[0] = s0 - beta * alpha * c
+
+
+def synthetic_state_dict(seed: int = 0, inv_s: float = 64.0, surface: bool = True) -> Dict[str, torch.Tensor]:
     """Random but well-conditioned weights with the checkpoint's keys/shapes.
 
     Linear weights ~ U(+-sqrt(6/(fan_in+fan_out))) (the reference's xavier init, transformer.py:73-76),
@@ -106,6 +138,8 @@ def synthetic_state_dict(seed: int = 0, inv_s: float = 20.0) -> Dict[str, torch.
             fan_in = int(torch.tensor(shp[1:]).prod()) if len(shp) > 1 else 1
             bound = math.sqrt(6.0 / (fan_in + fan_out))
             sd[k] = (torch.rand(shp, generator=gen) * 2 - 1) * bound
+    if surface:
+        _shape_surface_head(sd, gen)
     return sd
 
 
