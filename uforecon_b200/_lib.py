@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libuforecon_b200.so")
+LIB_PATH = os.environ.get("UFO_LIB_PATH", os.path.join(_HERE, "libuforecon_b200.so"))
 
 UFO_MAX_VIEWS = 10
 UFO_N_STAGES = 3

@@ -12,9 +12,10 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libuforecon_b200.so")
+OUT = os.environ.get("UFO_LIB_PATH", os.path.join(HERE, "libuforecon_b200.so"))
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
-OBJ_DIR = os.path.join(HERE, "build")
+OBJ_DIR = os.environ.get("UFO_OBJ_DIR", os.path.join(HERE, "build"))
+EXTRA = os.environ.get("UFO_NVCC_EXTRA", "").split()
 
 
 def _sources():
@@ -31,7 +32,7 @@ def needs_build() -> bool:
 
 def _compile(args):
     nvcc, src, obj, verbose = args
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+    cmd = [nvcc] + NVCC_FLAGS + EXTRA + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     return src, r.returncode, r.stdout + r.stderr
 

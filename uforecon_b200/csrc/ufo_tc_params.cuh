@@ -4,7 +4,11 @@
 
 namespace ufo {
 namespace tc {
-constexpr int kThreads = 512;
+#ifndef UFO_TC_GROUPS
+#define UFO_TC_GROUPS 4
+#endif
+constexpr int kGroups = UFO_TC_GROUPS;   // column groups per token row: warp w -> TMEM lanes 32*(w%4).., group w/4
+constexpr int kThreads = 128 * kGroups;
 constexpr uint32_t kChunk = 2048;   // bytes of one 8-column chunk of a 128-row operand tile
 }  // namespace tc
 
@@ -23,11 +27,12 @@ constexpr uint32_t V_WRAD = V_WML2 + 80 * 160 * 2;  // [16][160]  = [W0x | W0x]
 constexpr uint32_t V_WEND = V_WRAD + 16 * 160 * 2;  // 133120
 constexpr uint32_t V_X = V_WEND;                    // chunks 0..9   (token)
 constexpr uint32_t V_M = V_X + 10 * kChunk;         // chunks 10..19 (message / LN1 / LN2 output)
-constexpr uint32_t V_KV = V_M + 10 * kChunk;        // K',V' staging [4][128][80 B]; later H1 (20 chunks)
-constexpr uint32_t V_RED = V_KV + 20 * kChunk;      // float2 [4][128]
-constexpr uint32_t V_OMG = V_RED + 4096;            // float [128]
-constexpr uint32_t V_BAR = V_OMG + 512;
+constexpr uint32_t V_KV = V_M + 10 * kChunk;        // K',V' staging [8 heads][128][40 B]; later H1 (20 chunks)
+constexpr uint32_t V_RED = V_KV + 20 * kChunk;      // float2 [kGroups][128]  LayerNorm partials
+constexpr uint32_t V_OMG = V_RED + 8 * kGroups * 128;  // float [kGroups][128]   radiance-head partials
+constexpr uint32_t V_BAR = V_OMG + 4 * kGroups * 128;
 constexpr uint32_t V_SMEM = V_BAR + 64;
+static_assert(V_SMEM <= 232448, "view-stage shared memory exceeds the 227 KB opt-in limit");
 }  // namespace tc
 
 struct RayParams {
@@ -53,8 +58,8 @@ constexpr uint32_t R_RLO = R_Q + 12 * kChunk;         // r_lo 12 chunks
 constexpr uint32_t R_SLOTA = R_V + 12 * kChunk;       // Wqkv / Wmlp0 (streamed)
 constexpr uint32_t R_SLOTB = R_SLOTA + 176 * 176 * 2; // Wmerge / Wmlp2 (streamed)
 constexpr uint32_t R_WDEN = R_SLOTB + 96 * 176 * 2;   // resident
-constexpr uint32_t R_RED = R_WDEN + 2 * 32 * 96 * 2;  // float2 [4][128]
-constexpr uint32_t R_BAR = R_RED + 4096;
+constexpr uint32_t R_SCR = R_V + 4 * kChunk;          // LayerNorm / SRDF-tail partials: 8 KB inside V' chunks 4..7, dead then
+constexpr uint32_t R_BAR = R_WDEN + 2 * 32 * 96 * 2;
 constexpr uint32_t R_SMEM = R_BAR + 64;
 static_assert(R_SMEM <= 232448, "ray-stage shared memory exceeds the 227 KB opt-in limit");
 }  // namespace tc

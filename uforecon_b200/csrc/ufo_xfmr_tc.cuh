@@ -58,7 +58,108 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
   for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__device__ __forceinline__ float elu1_fast(float x) { return x > 0.f ? x + 1.f : __expf(x); }
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, float* v) {
+  uint32_t r[2];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr));
+  v[0] = __uint_as_float(r[0]);
+  v[1] = __uint_as_float(r[1]);
+}
+
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// elu(x) + 1 on a pair (packed fp32x2 multiply/add of sm_100, one MUFU.EX2 per element)
+__device__ __forceinline__ float2 elu1_2(float2 x) {
+  const float2 t = __fmul2_rn(x, make_float2(1.4426950408889634f, 1.4426950408889634f));
+  const float2 p = __fadd2_rn(x, make_float2(1.f, 1.f));
+  return make_float2(x.x > 0.f ? p.x : ex2_ftz(t.x), x.y > 0.f ? p.y : ex2_ftz(t.y));
+}
+__device__ __forceinline__ float elu1_fast(float x) { return x > 0.f ? x + 1.f : ex2_ftz(x * 1.4426950408889634f); }
+
+template <int N>
+struct IC {
+  static constexpr int value = N;
+};
+// call fn(IC<g>) with the warp-uniform column group as a compile-time constant (all chunk indices become static)
+#define UFO_G_DISPATCH(fn)  \
+  switch (g) {              \
+    case 0: fn(IC<0>{}); break; \
+    case 1: fn(IC<1>{}); break; \
+    case 2: fn(IC<2>{}); break; \
+    default: fn(IC<3>{}); break; \
+  }
+
+// 8 consecutive fp32 TMEM columns as 4 pairs
+__device__ __forceinline__ void tmem_ld8p(uint32_t taddr, float2* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = make_float2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+}
+
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack2v(float2 a) { return umma::pack2<BF16>(a.x, a.y); }
+
+template <bool BF16>
+__device__ __forceinline__ void st_chunk2(uint8_t* tile, int row, int chunk, const float2* v) {
+  uint4 u;
+  u.x = pack2v<BF16>(v[0]); u.y = pack2v<BF16>(v[1]); u.z = pack2v<BF16>(v[2]); u.w = pack2v<BF16>(v[3]);
+  *reinterpret_cast<uint4*>(tile_ptr(tile, row, chunk)) = u;
+}
+
+// relu on a pair after rounding to the operand format (relu commutes with the rounding)
+template <bool BF16>
+__device__ __forceinline__ uint32_t relu_pack2(float2 a) {
+  uint32_t u = pack2v<BF16>(a);
+  if (BF16) {
+    __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&u);
+    h = __hmax2(h, __float2bfloat162_rn(0.f));
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __half2 h = *reinterpret_cast<__half2*>(&u);
+  h = __hmax2(h, __float2half2_rn(0.f));
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// LayerNorm over a row whose columns are split over the 4 column groups: NCH chunks of 8 columns, group GG owns
+// chunks GG, GG+4, ...  ld: load the chunks and return this thread's partial (sum, sum of squares).
+template <int GG, int NCH>
+__device__ __forceinline__ float2 ln_load(uint32_t tcol, float2 (*v)[4]) {
+  constexpr int NI = (NCH - GG + 3) / 4;
+#pragma unroll
+  for (int i = 0; i < NI; ++i) tmem_ld8p(tcol + 8 * (GG + 4 * i), v[i]);
+  umma::tmem_ld_wait();
+  float2 s = make_float2(0.f, 0.f), q = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < NI; ++i)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      s = __fadd2_rn(s, v[i][k]);
+      q = __ffma2_rn(v[i][k], v[i][k], q);
+    }
+  return make_float2(s.x + s.y, q.x + q.y);
+}
+// (mean, rstd) of the row from the 4 partials
+__device__ __forceinline__ float2 ln_stats(const float2* red, int r, float inv_n) {
+  const float2 a0 = red[r], a1 = red[128 + r], a2 = red[256 + r], a3 = red[384 + r];
+  const float mean = ((a0.x + a1.x) + (a2.x + a3.x)) * inv_n;
+  const float var = fmaxf(((a0.y + a1.y) + (a2.y + a3.y)) * inv_n - mean * mean, 0.f);
+  return make_float2(mean, rsqrtf(var + 1e-5f));
+}
+// y = (v - mean) * rstd * w + b for one chunk, packed: a = w*rstd, y = v*a + (b - mean*a)
+__device__ __forceinline__ void ln_apply(const float2* v, float2 st, const float* w, const float* b, float2* o) {
+  const float2 rs = make_float2(st.y, st.y), nm = make_float2(-st.x, -st.x);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 a = __fmul2_rn(make_float2(w[2 * k], w[2 * k + 1]), rs);
+    const float2 c = __ffma2_rn(a, nm, make_float2(b[2 * k], b[2 * k + 1]));
+    o[k] = __ffma2_rn(v[k], a, c);
+  }
+}
 
 // split a float into a 16-bit head and the 16-bit remainder (hi + lo ~ x to ~2^-17 / 2^-22 relative)
 template <bool BF16>
@@ -218,8 +319,11 @@ k_view_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams p
           const float4* __restrict__ rgbm, const float4* __restrict__ dirs, long long P, int half,
           float* __restrict__ vout0, float4* __restrict__ radiance) {
   using namespace tc;
+  static_assert(kGroups == 4, "epilogues are written for 4 column groups (2 heads per thread)");
   constexpr int L = NV + 1, PPT = 128 / L, ROWS = PPT * L;
+  constexpr int NPF = (1280 + kThreads - 1) / kThreads;   // 16-byte token pieces per thread per tile
   constexpr uint32_t FMT = BF16 ? umma::kFmtBF16 : umma::kFmtF16;
+  constexpr uint32_t D_QKV = 0, D_RAD = 240, D_ML0 = 256, D_MRG = 416, D_ML2 = 0;   // TMEM columns
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   uint8_t* const smem = tc_smem;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + V_BAR);
@@ -256,119 +360,140 @@ k_view_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams p
   uint32_t ph = 0;
   const long long n_tiles = (P + PPT - 1) / PPT;
 
+  // 16-byte pieces of the token rows, prefetched one tile ahead into registers; the (row, chunk) -> (point, view)
+  // mapping of a piece does not depend on the tile
+  uint4 pf[NPF];
+  int pf_pt[NPF], pf_off[NPF];       // point within the tile (-1: no load), element offset inside the point's rows
+  uint32_t pf_dst[NPF];
+#pragma unroll
+  for (int k = 0; k < NPF; ++k) {
+    const int i = tid + k * kThreads;
+    const int rr = i & 127, c = i >> 7;
+    const int pr = rr / L, ll = rr - pr * L;
+    const bool on = (i < 1280) && (rr < ROWS) && (ll > 0);
+    pf_pt[k] = on ? pr : -1;
+    pf_off[k] = (ll - 1) * kDView + c * 8;
+    pf_dst[k] = (uint32_t)(c * kChunk + rr * 16);
+  }
+  auto prefetch = [&](long long tile) {
+    const long long pbase = tile * PPT;
+#pragma unroll
+    for (int k = 0; k < NPF; ++k) {
+      pf[k] = make_uint4(0, 0, 0, 0);
+      const long long p = pbase + pf_pt[k];
+      if (pf_pt[k] >= 0 && tile < n_tiles && p < P)
+        pf[k] = __ldg(reinterpret_cast<const uint4*>(tok + (size_t)tc_slot(p, half) * (NV * kDView) + pf_off[k]));
+    }
+  };
+  prefetch(blockIdx.x);
+
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long pbase = tile * PPT;
-    // ---- P0: token rows of this tile -> X (A operand, K = 80)
-    for (int i = tid; i < 128 * 10; i += kThreads) {
-      const int rr = i & 127, c = i >> 7;
-      const int pr = rr / L, ll = rr - pr * L;
-      if (rr < ROWS && ll > 0) {
-        const long long p = pbase + pr;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (p < P) v = __ldg(reinterpret_cast<const uint4*>(tok + ((size_t)tc_slot(p, half) * NV + (ll - 1)) * kDView) + c);
-        *reinterpret_cast<uint4*>(tile_ptr(smem + V_X, rr, c)) = v;
-      }
-    }
+    // ---- P0: token rows of this tile (prefetched) -> X (A operand, K = 80)
+#pragma unroll
+    for (int k = 0; k < NPF; ++k)
+      if (pf_pt[k] >= 0) *reinterpret_cast<uint4*>(smem + V_X + pf_dst[k]) = pf[k];
     const long long my_p = pbase + pl;
     const size_t my_slot = (size_t)tc_slot(my_p, half);
     const bool view_row = row_ok && l > 0 && my_p < P;
-    float4 my_dir = make_float4(0.f, 0.f, 0.f, 0.f);
-    float my_mask = 0.f;
-    if (g == 0 && view_row) {
-      my_dir = __ldg(dirs + my_slot * NV + (l - 1));
-      my_mask = __ldg(rgbm + my_slot * NV + (l - 1)).w;
-    }
     umma::fence_async_smem();
     umma::tc_fence_before();
     __syncthreads();
-    // ---- P1: q|k|v = X . Wqkv^T                                  (transformer.py:47)
+    // ---- P1: q|k|v = X . Wqkv^T (transformer.py:47); the x halves of mlp.0 and of the radiance head are issued
+    //      right behind it so that they run under the attention phase
     if (tid == 0) {
       umma::tc_fence_after();
-      issue_gemm_sub(tmem + 0, sm_base + V_X, sm_base + V_WQKV, 240, 0, 10, umma::make_idesc(128, 240, FMT, false, false), 0);
+      issue_gemm_sub(tmem + D_QKV, sm_base + V_X, sm_base + V_WQKV, 240, 0, 10, umma::make_idesc(128, 240, FMT, false, false), 0);
       umma::commit(bar);
+      issue_gemm_sub(tmem + D_ML0, sm_base + V_X, sm_base + V_WML0, 160, 0, 10, umma::make_idesc(128, 160, FMT, false, false), 0);
+      issue_gemm_sub(tmem + D_RAD, sm_base + V_X, sm_base + V_WRAD, 16, 0, 10, umma::make_idesc(128, 16, FMT, false, false), 0);
     }
+    prefetch(tile + gridDim.x);
+    float4 my_dir = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (view_row) my_dir = __ldg(dirs + my_slot * NV + (l - 1));
     umma::mbar_wait(bar, ph);
     ph ^= 1;
     umma::tc_fence_after();
-    // ---- P2: elu+1 on q, k; stage K', V' (16-bit) for the per-point attention   (linear_attention.py:36-41)
-    float qv[20];
+    // ---- P2: elu+1 on q, k; stage K', V' (16-bit) per head for the per-point attention   (linear_attention.py:36-41)
+    //      thread (row, g) owns heads 2g, 2g+1 = columns 20g .. 20g+19 of q, k and v
+    float2 qv[10];
     {
-      float kv[40];
-      umma::tmem_ld16(tlane + 20 * g, qv);
-      tmem_ld4(tlane + 20 * g + 16, qv + 16);
-      umma::tmem_ld16(tlane + 80 + 20 * g, kv);
-      tmem_ld4(tlane + 80 + 20 * g + 16, kv + 16);
-      umma::tmem_ld16(tlane + 160 + 20 * g, kv + 20);
-      tmem_ld4(tlane + 160 + 20 * g + 16, kv + 36);
+      float t[20];
+      umma::tmem_ld16(tlane + D_QKV + 20 * g, t);
+      tmem_ld4(tlane + D_QKV + 20 * g + 16, t + 16);
+      float kk[20];
+      umma::tmem_ld16(tlane + D_QKV + 80 + 20 * g, kk);
+      tmem_ld4(tlane + D_QKV + 80 + 20 * g + 16, kk + 16);
+      float vv[20];
+      umma::tmem_ld16(tlane + D_QKV + 160 + 20 * g, vv);
+      tmem_ld4(tlane + D_QKV + 160 + 20 * g + 16, vv + 16);
       umma::tmem_ld_wait();
+      uint32_t pk[10], pv[10];
 #pragma unroll
-      for (int i = 0; i < 20; ++i) {
-        qv[i] = elu1_fast(qv[i]);
-        kv[i] = elu1_fast(kv[i]);
+      for (int i = 0; i < 10; ++i) {
+        qv[i] = elu1_2(make_float2(t[2 * i], t[2 * i + 1]));
+        pk[i] = pack2v<BF16>(elu1_2(make_float2(kk[2 * i], kk[2 * i + 1])));
+        pv[i] = umma::pack2<BF16>(vv[2 * i], vv[2 * i + 1]);
       }
-      uint4* dst = reinterpret_cast<uint4*>(smem + V_KV + (size_t)(g * 128 + r) * 80);
+      // staging [8 heads][128 rows][k 10 | v 10] 16-bit = 40 B per (head, row)
 #pragma unroll
-      for (int i = 0; i < 5; ++i) dst[i] = pack8<BF16>(kv + 8 * i);
+      for (int hp = 0; hp < 2; ++hp) {
+        uint2* dst = reinterpret_cast<uint2*>(smem + V_KV + (size_t)((2 * g + hp) * 128 + r) * 40);
+        dst[0] = make_uint2(pk[5 * hp + 0], pk[5 * hp + 1]);
+        dst[1] = make_uint2(pk[5 * hp + 2], pk[5 * hp + 3]);
+        dst[2] = make_uint2(pk[5 * hp + 4], pv[5 * hp + 0]);
+        dst[3] = make_uint2(pv[5 * hp + 1], pv[5 * hp + 2]);
+        dst[4] = make_uint2(pv[5 * hp + 3], pv[5 * hp + 4]);
+      }
     }
     __syncthreads();
     // ---- P3: msg_l = sum_s (Q_l.K_s) V_s / (sum_s Q_l.K_s + 1e-6)  per head   (== Q (K^T V) Z, linear_attention.py:43-45)
     {
-      float msg[20];
-      if (row_ok) {
-        float den0 = 0.f, den1 = 0.f;
+      uint32_t mo[10];
 #pragma unroll
-        for (int i = 0; i < 20; ++i) msg[i] = 0.f;
+      for (int hp = 0; hp < 2; ++hp) {
+        float2 msg[5];
 #pragma unroll
-        for (int s = 0; s < L; ++s) {
-          const uint4* src = reinterpret_cast<const uint4*>(smem + V_KV + (size_t)(g * 128 + pl * L + s) * 80);
-          float kk[40];
+        for (int i = 0; i < 5; ++i) msg[i] = make_float2(0.f, 0.f);
+        if (row_ok) {
+          float den = 0.f;
 #pragma unroll
-          for (int i = 0; i < 5; ++i) {
-            const uint4 u = src[i];
-            const float2 a = unpack2<BF16>(u.x), b = unpack2<BF16>(u.y), c = unpack2<BF16>(u.z), d = unpack2<BF16>(u.w);
-            kk[8 * i + 0] = a.x; kk[8 * i + 1] = a.y; kk[8 * i + 2] = b.x; kk[8 * i + 3] = b.y;
-            kk[8 * i + 4] = c.x; kk[8 * i + 5] = c.y; kk[8 * i + 6] = d.x; kk[8 * i + 7] = d.y;
+          for (int s = 0; s < L; ++s) {
+            const uint2* src = reinterpret_cast<const uint2*>(smem + V_KV + (size_t)((2 * g + hp) * 128 + pl * L + s) * 40);
+            float2 kv[10];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+              const uint2 u = src[i];
+              kv[2 * i] = unpack2<BF16>(u.x);
+              kv[2 * i + 1] = unpack2<BF16>(u.y);
+            }
+            float2 acc = __fmul2_rn(qv[5 * hp], kv[0]);
+#pragma unroll
+            for (int a = 1; a < 5; ++a) acc = __ffma2_rn(qv[5 * hp + a], kv[a], acc);
+            const float sc = acc.x + acc.y;
+            den += sc;
+            const float2 sc2 = make_float2(sc, sc);
+#pragma unroll
+            for (int b = 0; b < 5; ++b) msg[b] = __ffma2_rn(sc2, kv[5 + b], msg[b]);
           }
-          float s0 = 0.f, s1 = 0.f;
+          const float zi = 1.f / (den + 1e-6f);
+          const float2 z2 = make_float2(zi, zi);
 #pragma unroll
-          for (int a = 0; a < 10; ++a) {
-            s0 = fmaf(qv[a], kk[a], s0);
-            s1 = fmaf(qv[10 + a], kk[10 + a], s1);
-          }
-          den0 += s0;
-          den1 += s1;
-#pragma unroll
-          for (int b = 0; b < 10; ++b) {
-            msg[b] = fmaf(s0, kk[20 + b], msg[b]);
-            msg[10 + b] = fmaf(s1, kk[30 + b], msg[10 + b]);
-          }
+          for (int b = 0; b < 5; ++b) msg[b] = __fmul2_rn(msg[b], z2);
         }
-        const float z0 = 1.f / (den0 + 1e-6f), z1 = 1.f / (den1 + 1e-6f);
 #pragma unroll
-        for (int b = 0; b < 10; ++b) {
-          msg[b] *= z0;
-          msg[10 + b] *= z1;
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 20; ++i) msg[i] = 0.f;
+        for (int b = 0; b < 5; ++b) mo[5 * hp + b] = pack2v<BF16>(msg[b]);
       }
       // columns 20g .. 20g+19 of the message tile: two full chunks and one half chunk
       const int c0 = (20 * g) >> 3;
-      if ((g & 1) == 0) {  // 20g % 8 == 0: chunks c0, c0+1 full, first half of c0+2
-        st_chunk<BF16>(smem + V_M, r, c0, msg);
-        st_chunk<BF16>(smem + V_M, r, c0 + 1, msg + 8);
-        uint2 h;
-        h.x = umma::pack2<BF16>(msg[16], msg[17]);
-        h.y = umma::pack2<BF16>(msg[18], msg[19]);
-        *reinterpret_cast<uint2*>(tile_ptr(smem + V_M, r, c0 + 2)) = h;
-      } else {             // 20g % 8 == 4: second half of c0, chunks c0+1, c0+2 full
-        uint2 h;
-        h.x = umma::pack2<BF16>(msg[0], msg[1]);
-        h.y = umma::pack2<BF16>(msg[2], msg[3]);
-        *reinterpret_cast<uint2*>(tile_ptr(smem + V_M, r, c0) + 8) = h;
-        st_chunk<BF16>(smem + V_M, r, c0 + 1, msg + 4);
-        st_chunk<BF16>(smem + V_M, r, c0 + 2, msg + 12);
+      if ((g & 1) == 0) {
+        *reinterpret_cast<uint4*>(tile_ptr(smem + V_M, r, c0)) = make_uint4(mo[0], mo[1], mo[2], mo[3]);
+        *reinterpret_cast<uint4*>(tile_ptr(smem + V_M, r, c0 + 1)) = make_uint4(mo[4], mo[5], mo[6], mo[7]);
+        *reinterpret_cast<uint2*>(tile_ptr(smem + V_M, r, c0 + 2)) = make_uint2(mo[8], mo[9]);
+      } else {
+        *reinterpret_cast<uint2*>(tile_ptr(smem + V_M, r, c0) + 8) = make_uint2(mo[0], mo[1]);
+        *reinterpret_cast<uint4*>(tile_ptr(smem + V_M, r, c0 + 1)) = make_uint4(mo[2], mo[3], mo[4], mo[5]);
+        *reinterpret_cast<uint4*>(tile_ptr(smem + V_M, r, c0 + 2)) = make_uint4(mo[6], mo[7], mo[8], mo[9]);
       }
     }
     umma::fence_async_smem();
@@ -377,7 +502,7 @@ k_view_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams p
     // ---- P4: merge                                                (transformer.py:55)
     if (tid == 0) {
       umma::tc_fence_after();
-      issue_gemm_sub(tmem + 256, sm_base + V_M, sm_base + V_WMRG, 80, 0, 10, umma::make_idesc(128, 80, FMT, false, false), 0);
+      issue_gemm_sub(tmem + D_MRG, sm_base + V_M, sm_base + V_WMRG, 80, 0, 10, umma::make_idesc(128, 80, FMT, false, false), 0);
       umma::commit(bar);
     }
     umma::mbar_wait(bar, ph);
@@ -385,67 +510,47 @@ k_view_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams p
     umma::tc_fence_after();
     // ---- P5: LayerNorm 1 -> second half of the concat operand     (transformer.py:56)
     {
-      float v[24];
-      int nc = 0;
+      auto ln1 = [&](auto GGc) {
+        constexpr int GG = decltype(GGc)::value;
+        constexpr int NI = (10 - GG + 3) / 4;
+        float2 v[NI][4];
+        red[GG * 128 + r] = ln_load<GG, 10>(tlane + D_MRG, v);
+        __syncthreads();
+        const float2 st = ln_stats(red, r, 1.f / 80.f);
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const int c = g + 4 * i;
-        if (c < 10) {
-          umma::tmem_ld8(tlane + 256 + 8 * c, v + 8 * i);
-          nc = i + 1;
+        for (int i = 0; i < NI; ++i) {
+          constexpr int dummy = 0;
+          (void)dummy;
+          const int c = GG + 4 * i;
+          float2 o[4];
+          ln_apply(v[i], st, prm.n1w + 8 * c, prm.n1b + 8 * c, o);
+          st_chunk2<BF16>(smem + V_M, r, c, o);
         }
-      }
-      umma::tmem_ld_wait();
-      float s = 0.f, ss = 0.f;
-#pragma unroll
-      for (int i = 0; i < 24; ++i)
-        if (i < 8 * nc) {
-          s += v[i];
-          ss = fmaf(v[i], v[i], ss);
-        }
-      red[g * 128 + r] = make_float2(s, ss);
-      __syncthreads();
-      const float2 a0 = red[r], a1 = red[128 + r], a2 = red[256 + r], a3 = red[384 + r];
-      const float mean = (a0.x + a1.x + a2.x + a3.x) * (1.f / 80.f);
-      const float var = fmaxf((a0.y + a1.y + a2.y + a3.y) * (1.f / 80.f) - mean * mean, 0.f);
-      const float rstd = rsqrtf(var + 1e-5f);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const int c = g + 4 * i;
-        if (c < 10) {
-          float o[8];
-  #pragma unroll
-          for (int k = 0; k < 8; ++k) o[k] = (v[8 * i + k] - mean) * rstd * prm.n1w[8 * c + k] + prm.n1b[8 * c + k];
-          st_chunk<BF16>(smem + V_M, r, c, o);
-        }
-      }
+      };
+      UFO_G_DISPATCH(ln1)
     }
     umma::fence_async_smem();
     umma::tc_fence_before();
     __syncthreads();
-    // ---- P6: mlp.0 on [x | msg]                                   (transformer.py:57)
+    // ---- P6: message half of mlp.0 on top of the x half issued in P1   (transformer.py:57)
     if (tid == 0) {
       umma::tc_fence_after();
-      issue_gemm_sub(tmem + 0, sm_base + V_X, sm_base + V_WML0, 160, 0, 20, umma::make_idesc(128, 160, FMT, false, false), 0);
+      issue_gemm_sub(tmem + D_ML0, sm_base + V_M, sm_base + V_WML0 + 10 * (160 * 16), 160, 0, 10, umma::make_idesc(128, 160, FMT, false, false), 1);
       umma::commit(bar);
     }
     umma::mbar_wait(bar, ph);
     ph ^= 1;
     umma::tc_fence_after();
-    // ---- P7: ReLU -> H1 operand (aliases the K'/V' staging)
+    // ---- P7: ReLU -> H1 operand (aliases the K'/V' staging); group g owns chunks g, g+4, .., g+16
     {
+      float2 v[5][4];
 #pragma unroll
-      for (int i = 0; i < 5; ++i) {
-        const int c = g + 4 * i;
-        if (c < 20) {
-          float v[8];
-          umma::tmem_ld8(tlane + 8 * c, v);
-          umma::tmem_ld_wait();
-  #pragma unroll
-          for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
-          st_chunk<BF16>(smem + V_KV, r, c, v);
-        }
-      }
+      for (int i = 0; i < 5; ++i) tmem_ld8p(tlane + D_ML0 + 8 * (g + 4 * i), v[i]);
+      umma::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 5; ++i)
+        *reinterpret_cast<uint4*>(tile_ptr(smem + V_KV, r, g + 4 * i)) =
+            make_uint4(relu_pack2<BF16>(v[i][0]), relu_pack2<BF16>(v[i][1]), relu_pack2<BF16>(v[i][2]), relu_pack2<BF16>(v[i][3]));
     }
     umma::fence_async_smem();
     umma::tc_fence_before();
@@ -453,7 +558,7 @@ k_view_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams p
     // ---- P8: mlp.2
     if (tid == 0) {
       umma::tc_fence_after();
-      issue_gemm_sub(tmem + 256, sm_base + V_KV, sm_base + V_WML2, 80, 0, 20, umma::make_idesc(128, 80, FMT, false, false), 0);
+      issue_gemm_sub(tmem + D_ML2, sm_base + V_KV, sm_base + V_WML2, 80, 0, 20, umma::make_idesc(128, 80, FMT, false, false), 0);
       umma::commit(bar);
     }
     umma::mbar_wait(bar, ph);
@@ -462,127 +567,121 @@ k_view_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams p
     // ---- P9: LayerNorm 2; token 0: out = view_token + LN2 -> vout0 (fp32); view rows: LN2 -> operand for the
     //      radiance head (x + LN2 is applied inside the head's GEMM: W0x.x + W0x.LN2)
     {
-      float v[24];
-      int nc = 0;
+      auto ln2 = [&](auto GGc) {
+        constexpr int GG = decltype(GGc)::value;
+        constexpr int NI = (10 - GG + 3) / 4;
+        float2 v[NI][4];
+        red[GG * 128 + r] = ln_load<GG, 10>(tlane + D_ML2, v);
+        __syncthreads();
+        const float2 st = ln_stats(red, r, 1.f / 80.f);
+        const bool tok0 = row_ok && l == 0 && my_p < P;
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const int c = g + 4 * i;
-        if (c < 10) {
-          umma::tmem_ld8(tlane + 256 + 8 * c, v + 8 * i);
-          nc = i + 1;
-        }
-      }
-      umma::tmem_ld_wait();
-      float s = 0.f, ss = 0.f;
-#pragma unroll
-      for (int i = 0; i < 24; ++i)
-        if (i < 8 * nc) {
-          s += v[i];
-          ss = fmaf(v[i], v[i], ss);
-        }
-      red[g * 128 + r] = make_float2(s, ss);
-      __syncthreads();
-      const float2 a0 = red[r], a1 = red[128 + r], a2 = red[256 + r], a3 = red[384 + r];
-      const float mean = (a0.x + a1.x + a2.x + a3.x) * (1.f / 80.f);
-      const float var = fmaxf((a0.y + a1.y + a2.y + a3.y) * (1.f / 80.f) - mean * mean, 0.f);
-      const float rstd = rsqrtf(var + 1e-5f);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const int c = g + 4 * i;
-        if (c < 10) {
-          float o[8];
-  #pragma unroll
-          for (int k = 0; k < 8; ++k) o[k] = (v[8 * i + k] - mean) * rstd * prm.n2w[8 * c + k] + prm.n2b[8 * c + k];
-          st_chunk<BF16>(smem + V_M, r, c, o);
-          if (row_ok && l == 0 && my_p < P) {
+        for (int i = 0; i < NI; ++i) {
+          const int c = GG + 4 * i;
+          float2 o[4];
+          ln_apply(v[i], st, prm.n2w + 8 * c, prm.n2b + 8 * c, o);
+          st_chunk2<BF16>(smem + V_M, r, c, o);
+          if (tok0) {
             float4* dst = reinterpret_cast<float4*>(vout0 + my_slot * kDView + 8 * c);
-            dst[0] = make_float4(prm.vtok[8 * c] + o[0], prm.vtok[8 * c + 1] + o[1], prm.vtok[8 * c + 2] + o[2], prm.vtok[8 * c + 3] + o[3]);
-            dst[1] = make_float4(prm.vtok[8 * c + 4] + o[4], prm.vtok[8 * c + 5] + o[5], prm.vtok[8 * c + 6] + o[6], prm.vtok[8 * c + 7] + o[7]);
+            dst[0] = make_float4(prm.vtok[8 * c] + o[0].x, prm.vtok[8 * c + 1] + o[0].y, prm.vtok[8 * c + 2] + o[1].x, prm.vtok[8 * c + 3] + o[1].y);
+            dst[1] = make_float4(prm.vtok[8 * c + 4] + o[2].x, prm.vtok[8 * c + 5] + o[2].y, prm.vtok[8 * c + 6] + o[3].x, prm.vtok[8 * c + 7] + o[3].y);
           }
         }
-      }
+      };
+      UFO_G_DISPATCH(ln2)
     }
     umma::fence_async_smem();
     umma::tc_fence_before();
     __syncthreads();
-    // ---- P10: radiance head layer 0 on [x | LN2]                  (ray_transformer.py:159-163,313)
+    // ---- P10: LN2 half of the radiance head's first layer        (ray_transformer.py:159-163,313)
     if (tid == 0) {
       umma::tc_fence_after();
-      issue_gemm_sub(tmem + 384, sm_base + V_X, sm_base + V_WRAD, 16, 0, 20, umma::make_idesc(128, 16, FMT, false, false), 0);
+      issue_gemm_sub(tmem + D_RAD, sm_base + V_M, sm_base + V_WRAD + 10 * (16 * 16), 16, 0, 10, umma::make_idesc(128, 16, FMT, false, false), 1);
       umma::commit(bar);
     }
     umma::mbar_wait(bar, ph);
     ph ^= 1;
     umma::tc_fence_after();
-    // ---- P11: head tail, masked softmax over views, colour blend  (ray_transformer.py:313-320)
-    if (g == 0) {
+    // ---- P11: head tail 16 -> 8 -> 1 (hidden units g and g+4 per thread), masked softmax, colour blend
+    {
       float h[16];
-      umma::tmem_ld16(tlane + 384, h);
+      umma::tmem_ld16(tlane + D_RAD, h);
       umma::tmem_ld_wait();
-      float w = -1e9f;
-      if (view_row && my_mask != 0.f) {
+      auto tail = [&](auto GGc) {
+        constexpr int GG = decltype(GGc)::value;
 #pragma unroll
         for (int o = 0; o < 16; ++o)
           h[o] = fmaxf(h[o] + prm.rb0[o] + prm.rw0d[o][0] * my_dir.x + prm.rw0d[o][1] * my_dir.y + prm.rw0d[o][2] * my_dir.z, 0.f);
-        float acc = prm.rb4;
+        float part = 0.f;
 #pragma unroll
-        for (int o = 0; o < 8; ++o) {
-          float a = prm.rb2[o];
+        for (int j = 0; j < 2; ++j) {
+          constexpr int dummy = 0;
+          (void)dummy;
+          const int o = GG + 4 * j;
+          float a0 = prm.rb2[o], a1 = 0.f;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) a = fmaf(h[i], prm.rw2[o][i], a);
-          acc = fmaf(fmaxf(a, 0.f), prm.rw4[o], acc);
+          for (int i = 0; i < 16; i += 2) {
+            a0 = fmaf(h[i], prm.rw2[o][i], a0);
+            a1 = fmaf(h[i + 1], prm.rw2[o][i + 1], a1);
+          }
+          part = fmaf(fmaxf(a0 + a1, 0.f), prm.rw4[o], part);
         }
-        w = acc;
-      }
-      omg[r] = w;
+        omg[GG * 128 + r] = part;
+      };
+      UFO_G_DISPATCH(tail)
     }
     umma::tc_fence_before();
     __syncthreads();
     if (tid < PPT && pbase + tid < P) {
       const size_t p = (size_t)tc_slot(pbase + tid, half);
       float om[NV];
+      float4 col[NV];
       float mx = -INFINITY;
 #pragma unroll
       for (int n = 0; n < NV; ++n) {
-        om[n] = omg[tid * L + 1 + n];
+        col[n] = __ldg(rgbm + p * NV + n);
+        const int rr = tid * L + 1 + n;
+        const float w = prm.rb4 + ((omg[rr] + omg[128 + rr]) + (omg[256 + rr] + omg[384 + rr]));
+        om[n] = (col[n].w == 0.f) ? -1e9f : w;                     // ray_transformer.py:316
         mx = fmaxf(mx, om[n]);
       }
       float den = 0.f;
 #pragma unroll
       for (int n = 0; n < NV; ++n) {
-        om[n] = __expf(om[n] - mx);
+        om[n] = ex2_ftz((om[n] - mx) * 1.4426950408889634f);
         den += om[n];
       }
       float cr = 0.f, cg = 0.f, cb = 0.f;
 #pragma unroll
       for (int n = 0; n < NV; ++n) {
-        const float4 c = __ldg(rgbm + p * NV + n);
         const float pw = om[n] / den;
-        cr = fmaf(c.x, pw, cr);
-        cg = fmaf(c.y, pw, cg);
-        cb = fmaf(c.z, pw, cb);
+        cr = fmaf(col[n].x, pw, cr);
+        cg = fmaf(col[n].y, pw, cg);
+        cb = fmaf(col[n].z, pw, cb);
       }
       radiance[p] = make_float4(cr, cg, cb, 0.f);
     }
-    // the next tile's P0 writes X only after this tile's last MMA (P10) has completed: guaranteed by the wait above
+    // the next tile's P0 writes X only after this tile's last MMA (P10) has completed: guaranteed by the wait above;
+    // omg is next written after several more block-wide barriers
   }
   umma::tc_fence_before();
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc(tmem, 512);
 }
 
-
 // =================================================================================================
 // ray stage: density_ray_transformer (d = 88) + DensityMLP, tokens = samples of one ray
 // =================================================================================================
-// SN = 128: one ray per tile; SN = 64: two rays per tile.  vout0 [P][80] fp32 (token-0 output of the view
-// stage), pe_table [128][8], srdf [P] out, ray_out [P][88] optional tap.
+// SN = 128: one ray per tile; SN = 64: two rays per tile.  vout0 [slots][80] fp32 (token-0 output of the view
+// stage), pe_table [128][8], perm [R][128] (fine pass), srdf [P] out, ray_out [P][88] optional tap.
 template <int SN, bool BF16>
 __global__ void __launch_bounds__(tc::kThreads, 1)
 k_ray_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams prm, const float* __restrict__ vout0,
          const float* __restrict__ pe_table, const uint8_t* __restrict__ perm, long long P, float* __restrict__ srdf,
          float* __restrict__ ray_out) {
   using namespace tc;
+  constexpr int G = kGroups;
+  static_assert(kGroups == 4, "epilogues are written for 4 column groups");
   constexpr uint32_t FMT = BF16 ? umma::kFmtBF16 : umma::kFmtF16;
   constexpr int NSEQ = 128 / SN;
   extern __shared__ __align__(1024) uint8_t tc_smem[];
@@ -591,7 +690,7 @@ k_ray_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams prm
   uint64_t* barA = reinterpret_cast<uint64_t*>(smem + R_BAR + 8);   // slot A filled
   uint64_t* barB = reinterpret_cast<uint64_t*>(smem + R_BAR + 16);  // slot B filled
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + R_BAR + 24);
-  float2* red = reinterpret_cast<float2*>(smem + R_RED);
+  float2* red = reinterpret_cast<float2*>(smem + R_SCR);            // [G][128] partials (inside dead V' chunks)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, g = warp >> 2, r = q * 32 + lane;
   const long long n_tiles = (P + 127) / 128;
@@ -616,6 +715,35 @@ k_ray_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams prm
     float one[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};                    // ones columns: D rows 88..95 = sum_s K'_s
     st_chunk<BF16>(smem + R_V, r, 11, one);
   }
+  const uint32_t tmem_dummy = 0;
+  (void)tmem_dummy;
+  // x of a tile: token-0 output of the view stage at slot(ray, evaluation index) -> 16-bit A operand chunks 0..9
+  auto in_row_of = [&](long long tile) -> long long {
+    const long long prow = tile * 128 + r;
+    if (prow >= P) return -1;
+    return (SN == kNC) ? tc_slot(prow, 0) : tile * 128 + (perm ? (long long)perm[prow] : (long long)r);
+  };
+  auto load_x = [&](long long tile) {
+    const long long ir = in_row_of(tile);
+    constexpr int NI = (10 + G - 1) / G;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int c = g + G * i;
+      if (c < 10) {
+        float v[8];
+        if (ir >= 0) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(vout0 + (size_t)ir * kDView + 8 * c));
+          const float4 b = __ldg(reinterpret_cast<const float4*>(vout0 + (size_t)ir * kDView + 8 * c + 4));
+          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = 0.f;
+        }
+        st_chunk<BF16>(smem + R_X, r, c, v);
+      }
+    }
+  };
+  if ((long long)blockIdx.x < n_tiles) load_x(blockIdx.x);
   umma::fence_async_smem();
   umma::tc_fence_before();
   __syncthreads();
@@ -634,30 +762,9 @@ k_ray_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams prm
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long prow = tile * 128 + r;           // this thread's token: ray prow/SN, sorted sample prow%SN
     const bool row_ok = prow < P;
-    // its view-stage result lives at slot(ray, evaluation index): coarse pass = sample index, fine pass = perm
-    size_t in_row = 0;
-    if (row_ok) in_row = (SN == kNC) ? (size_t)tc_slot(prow, 0) : (size_t)(tile * 128 + (perm ? (int)perm[prow] : r));
-    // ---- R0: x = token-0 output of the view stage -> 16-bit A operand (columns 80..87 = order PE, constant)
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const int c = g + 4 * i;
-      if (c < 10) {
-        float v[8];
-        if (row_ok) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(vout0 + in_row * kDView + 8 * c));
-          const float4 b = __ldg(reinterpret_cast<const float4*>(vout0 + in_row * kDView + 8 * c + 4));
-          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        } else {
-  #pragma unroll
-          for (int k = 0; k < 8; ++k) v[k] = 0.f;
-        }
-        st_chunk<BF16>(smem + R_X, r, c, v);
-      }
-    }
-    umma::fence_async_smem();
-    umma::tc_fence_before();
-    __syncthreads();
-    // ---- R1: q|k|v = x . Wqkv^T   (K = 96: columns 88..95 hit zero weight columns)
+    const long long in_row = in_row_of(tile);
+    // ---- R1: q|k|v = x . Wqkv^T   (K = 96: columns 88..95 hit zero weight columns); x was staged by the previous
+    //      iteration (or the prologue) and fenced there
     if (tid == 0) {
       umma::mbar_wait(barA, phA);
       phA ^= 1;
@@ -671,24 +778,29 @@ k_ray_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams prm
     umma::tc_fence_after();
     if (tid == 0) bulk_load(smem + R_SLOTA, wimg + RW_ML0, 176 * 176 * 2, barA);   // slot A is free again
     // ---- R2: Q' = elu(q)+1, K' = elu(k)+1, V' = v  -> 16-bit operand tiles    (linear_attention.py:36-41)
+    {
+      auto r2 = [&](auto GGc) {
+        constexpr int GG = decltype(GGc)::value;
+        constexpr int NI = (11 - GG + 3) / 4;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const int c = g + 4 * i;
-      if (c < 11) {
-        float a[8], b[8], d[8];
-        umma::tmem_ld8(tlane + D_QKV + 8 * c, a);
-        umma::tmem_ld8(tlane + D_QKV + 88 + 8 * c, b);
-        umma::tmem_ld8(tlane + D_QKV + 176 + 8 * c, d);
-        umma::tmem_ld_wait();
-  #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          a[k] = elu1_fast(a[k]);
-          b[k] = elu1_fast(b[k]);
+        for (int i = 0; i < NI; ++i) {
+          const int c = GG + 4 * i;
+          float2 a[4], b[4], d[4];
+          tmem_ld8p(tlane + D_QKV + 8 * c, a);
+          tmem_ld8p(tlane + D_QKV + 88 + 8 * c, b);
+          tmem_ld8p(tlane + D_QKV + 176 + 8 * c, d);
+          umma::tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            a[k] = elu1_2(a[k]);
+            b[k] = elu1_2(b[k]);
+          }
+          st_chunk2<BF16>(smem + R_Q, r, c, a);
+          st_chunk2<BF16>(smem + R_K, r, c, b);
+          st_chunk2<BF16>(smem + R_V, r, c, d);
         }
-        st_chunk<BF16>(smem + R_Q, r, c, a);
-        st_chunk<BF16>(smem + R_K, r, c, b);
-        st_chunk<BF16>(smem + R_V, r, c, d);
-      }
+      };
+      UFO_G_DISPATCH(r2)
     }
     umma::fence_async_smem();
     umma::tc_fence_before();
@@ -711,29 +823,30 @@ k_ray_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams prm
     umma::mbar_wait(bar, ph);
     ph ^= 1;
     umma::tc_fence_after();
-    // ---- R4: block-diagonal KV (per head 11x11) + the K-sum row as the B operand of the message GEMM
+    // ---- R4: block-diagonal KV (per head 11x11) + per-head K-sum rows as the B operand of the message GEMM
     if (r < 96) {
+      // rows 0..87: KV_h of the row's head; row 88+h: the K-sum of head h (per-head normaliser)
+      const int hr = r < 88 ? r / 11 : r - 88;
+      auto r4 = [&](auto GGc) {
+        constexpr int GG = decltype(GGc)::value;
 #pragma unroll
-      for (int sq = 0; sq < NSEQ; ++sq) {
-        uint8_t* kvbd = smem + (sq == 0 ? R_K : R_V);        // [96 rows b][96 cols a], chunk stride 96*16
+        for (int sq = 0; sq < NSEQ; ++sq) {
+          uint8_t* kvbd = smem + (sq == 0 ? R_K : R_V);        // [96 rows b][96 cols a], chunk stride 96*16
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          const int c = g + 4 * i;
-          if (c < 12) {
+          for (int i = 0; i < 3; ++i) {
+            constexpr int dummy = 0;
+            (void)dummy;
+            const int c = GG + 4 * i;
             float v[8];
             umma::tmem_ld8(tlane + D_KV + 96 * sq + 8 * c, v);
             umma::tmem_ld_wait();
-  #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const int a = 8 * c + k;
-              // rows 0..87: KV_h of the row's head; row 88+h: the K-sum of head h (per-head normaliser)
-            const bool keep = (a < 88) && ((a / 11) == (r < 88 ? r / 11 : r - 88));
-              v[k] = keep ? v[k] : 0.f;
-            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = ((8 * c + k) < 88 && ((8 * c + k) / 11) == hr) ? v[k] : 0.f;
             *reinterpret_cast<uint4*>(kvbd + c * (96 * 16) + r * 16) = pack8<BF16>(v);
           }
         }
-      }
+      };
+      UFO_G_DISPATCH(r4)
     }
     umma::fence_async_smem();
     umma::tc_fence_before();
@@ -758,26 +871,21 @@ k_ray_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams prm
       umma::tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 8; ++j) zr[j] = 1.f / (zr[j] + 1e-6f);
+      auto r6 = [&](auto GGc) {
+        constexpr int GG = decltype(GGc)::value;
+        constexpr int NI = (11 - GG + 3) / 4;
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const int c = g + 4 * i;
-        if (c < 11) {
+        for (int i = 0; i < NI; ++i) {
+          const int c = GG + 4 * i;
           float v[8];
           umma::tmem_ld8(dm + 8 * c, v);
           umma::tmem_ld_wait();
-          // the 8 columns of a chunk belong to at most two heads (11 channels each)
-          const int h0 = (8 * c) / 11, h1 = (8 * c + 7) / 11, split = 11 * h1;
-          float z0 = zr[0], z1 = zr[0];
 #pragma unroll
-          for (int j = 1; j < 8; ++j) {
-            z0 = (j == h0) ? zr[j] : z0;
-            z1 = (j == h1) ? zr[j] : z1;
-          }
-#pragma unroll
-          for (int k = 0; k < 8; ++k) v[k] *= ((8 * c + k) < split) ? z0 : z1;
+          for (int k = 0; k < 8; ++k) v[k] *= zr[(8 * c + k) / 11];      // static index: head of column 8c+k
           st_chunk<BF16>(smem + R_M, r, c, v);
         }
-      }
+      };
+      UFO_G_DISPATCH(r6)
     }
     umma::fence_async_smem();
     umma::tc_fence_before();
@@ -796,40 +904,22 @@ k_ray_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams prm
     if (tid == 0) bulk_load(smem + R_SLOTB, wimg + RW_ML2, 96 * 176 * 2, barB);
     // ---- R8: LayerNorm 1 -> second half of the concat operand
     {
-      float v[24];
-      int nc = 0;
+      auto ln1 = [&](auto GGc) {
+        constexpr int GG = decltype(GGc)::value;
+        constexpr int NI = (11 - GG + 3) / 4;
+        float2 v[NI][4];
+        red[GG * 128 + r] = ln_load<GG, 11>(tlane + D_MRG, v);
+        __syncthreads();
+        const float2 st = ln_stats(red, r, 1.f / 88.f);
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const int c = g + 4 * i;
-        if (c < 11) {
-          umma::tmem_ld8(tlane + D_MRG + 8 * c, v + 8 * i);
-          nc = i + 1;
+        for (int i = 0; i < NI; ++i) {
+          const int c = GG + 4 * i;
+          float2 o[4];
+          ln_apply(v[i], st, prm.n1w + 8 * c, prm.n1b + 8 * c, o);
+          st_chunk2<BF16>(smem + R_M, r, c, o);
         }
-      }
-      umma::tmem_ld_wait();
-      float s = 0.f, ss = 0.f;
-#pragma unroll
-      for (int i = 0; i < 24; ++i)
-        if (i < 8 * nc) {
-          s += v[i];
-          ss = fmaf(v[i], v[i], ss);
-        }
-      red[g * 128 + r] = make_float2(s, ss);
-      __syncthreads();
-      const float2 a0 = red[r], a1 = red[128 + r], a2 = red[256 + r], a3 = red[384 + r];
-      const float mean = (a0.x + a1.x + a2.x + a3.x) * (1.f / 88.f);
-      const float var = fmaxf((a0.y + a1.y + a2.y + a3.y) * (1.f / 88.f) - mean * mean, 0.f);
-      const float rstd = rsqrtf(var + 1e-5f);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const int c = g + 4 * i;
-        if (c < 11) {
-          float o[8];
-  #pragma unroll
-          for (int k = 0; k < 8; ++k) o[k] = (v[8 * i + k] - mean) * rstd * prm.n1w[8 * c + k] + prm.n1b[8 * c + k];
-          st_chunk<BF16>(smem + R_M, r, c, o);
-        }
-      }
+      };
+      UFO_G_DISPATCH(ln1)
     }
     umma::fence_async_smem();
     umma::tc_fence_before();
@@ -845,19 +935,26 @@ k_ray_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams prm
     umma::mbar_wait(bar, ph);
     ph ^= 1;
     umma::tc_fence_after();
-    if (tid == 0 && tile + (long long)gridDim.x < n_tiles) bulk_load(smem + R_SLOTA, wimg + RW_QKV, 272 * 96 * 2, barA);
+    const bool has_next = tile + (long long)gridDim.x < n_tiles;
+    if (tid == 0 && has_next) bulk_load(smem + R_SLOTA, wimg + RW_QKV, 272 * 96 * 2, barA);
+    // x of the next tile: the concat operand is free from here on; its loads complete under the rest of this tile
+    if (has_next) load_x(tile + gridDim.x);
     // ---- R10: ReLU -> H1 operand (aliases K'/V' chunks 0..21)
+    {
+      auto r10 = [&](auto GGc) {
+        constexpr int GG = decltype(GGc)::value;
+        constexpr int NI = (22 - GG + 3) / 4;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      const int c = g + 4 * i;
-      if (c < 22) {
-        float v[8];
-        umma::tmem_ld8(tlane + D_ML0 + 8 * c, v);
-        umma::tmem_ld_wait();
-  #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
-        st_chunk<BF16>(smem + R_K, r, c, v);
-      }
+        for (int i = 0; i < NI; ++i) {
+          const int c = GG + 4 * i;
+          float2 v[4];
+          tmem_ld8p(tlane + D_ML0 + 8 * c, v);
+          umma::tmem_ld_wait();
+          *reinterpret_cast<uint4*>(tile_ptr(smem + R_K, r, c)) =
+              make_uint4(relu_pack2<BF16>(v[0]), relu_pack2<BF16>(v[1]), relu_pack2<BF16>(v[2]), relu_pack2<BF16>(v[3]));
+        }
+      };
+      UFO_G_DISPATCH(r10)
     }
     umma::fence_async_smem();
     umma::tc_fence_before();
@@ -873,72 +970,63 @@ k_ray_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams prm
     umma::mbar_wait(bar, ph);
     ph ^= 1;
     umma::tc_fence_after();
-    if (tid == 0 && tile + (long long)gridDim.x < n_tiles) bulk_load(smem + R_SLOTB, wimg + RW_MRG, 96 * 96 * 2, barB);
+    if (tid == 0 && has_next) bulk_load(smem + R_SLOTB, wimg + RW_MRG, 96 * 96 * 2, barB);
     // ---- R12: LayerNorm 2, residual in fp32 from the fp32 input, split hi/lo for the SRDF head
     {
-      float v[24];
-      int nc = 0;
+      auto ln2 = [&](auto GGc) {
+        constexpr int GG = decltype(GGc)::value;
+        constexpr int NI = (11 - GG + 3) / 4;
+        float2 v[NI][4];
+        red[GG * 128 + r] = ln_load<GG, 11>(tlane + D_ML2, v);
+        __syncthreads();
+        const float2 st = ln_stats(red, r, 1.f / 88.f);
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const int c = g + 4 * i;
-        if (c < 11) {
-          umma::tmem_ld8(tlane + D_ML2 + 8 * c, v + 8 * i);
-          nc = i + 1;
-        }
-      }
-      umma::tmem_ld_wait();
-      float s = 0.f, ss = 0.f;
-#pragma unroll
-      for (int i = 0; i < 24; ++i)
-        if (i < 8 * nc) {
-          s += v[i];
-          ss = fmaf(v[i], v[i], ss);
-        }
-      red[g * 128 + r] = make_float2(s, ss);
-      __syncthreads();
-      const float2 a0 = red[r], a1 = red[128 + r], a2 = red[256 + r], a3 = red[384 + r];
-      const float mean = (a0.x + a1.x + a2.x + a3.x) * (1.f / 88.f);
-      const float var = fmaxf((a0.y + a1.y + a2.y + a3.y) * (1.f / 88.f) - mean * mean, 0.f);
-      const float rstd = rsqrtf(var + 1e-5f);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const int c = g + 4 * i;
-        if (c < 12) {
+        for (int i = 0; i < 3; ++i) {
+          constexpr int dummy = 0;
+          (void)dummy;
+          const int c = GG + 4 * i;
           float hi[8], lo[8];
           if (c < 11) {
+            float2 o2[4];
+            ln_apply(v[i < NI ? i : 0], st, prm.n2w + 8 * (c < 11 ? c : 0), prm.n2b + 8 * (c < 11 ? c : 0), o2);
             float x[8];
             if (c < 10) {
               if (row_ok) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(vout0 + in_row * kDView + 8 * c));
-                const float4 b = __ldg(reinterpret_cast<const float4*>(vout0 + in_row * kDView + 8 * c + 4));
+                const float4 a = __ldg(reinterpret_cast<const float4*>(vout0 + (size_t)in_row * kDView + 8 * c));
+                const float4 b = __ldg(reinterpret_cast<const float4*>(vout0 + (size_t)in_row * kDView + 8 * c + 4));
                 x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
               } else {
-  #pragma unroll
+#pragma unroll
                 for (int k = 0; k < 8; ++k) x[k] = 0.f;
               }
             } else {
-  #pragma unroll
+#pragma unroll
               for (int k = 0; k < 8; ++k) x[k] = __ldg(pe_table + (r % SN) * 8 + k);
             }
             float o[8];
-  #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              o[k] = x[k] + ((v[8 * i + k] - mean) * rstd * prm.n2w[8 * c + k] + prm.n2b[8 * c + k]);
-              split_hi_lo<BF16>(o[k], hi[k], lo[k]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              o[2 * k] = x[2 * k] + o2[k].x;
+              o[2 * k + 1] = x[2 * k + 1] + o2[k].y;
             }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) split_hi_lo<BF16>(o[k], hi[k], lo[k]);
             if (ray_out != nullptr && row_ok) {
               float4* dst = reinterpret_cast<float4*>(ray_out + (size_t)prow * kDRay + 8 * c);
               dst[0] = make_float4(o[0], o[1], o[2], o[3]);
               dst[1] = make_float4(o[4], o[5], o[6], o[7]);
             }
           } else {
-  #pragma unroll
+#pragma unroll
             for (int k = 0; k < 8; ++k) hi[k] = lo[k] = 0.f;
           }
-          st_chunk<BF16>(smem + R_Q, r, c, hi);
-          st_chunk<BF16>(smem + R_RLO, r, c, lo);
+          if (c < 12) {
+            st_chunk<BF16>(smem + R_Q, r, c, hi);
+            st_chunk<BF16>(smem + R_RLO, r, c, lo);
+          }
         }
-      }
+      };
+      UFO_G_DISPATCH(ln2)
     }
     umma::fence_async_smem();
     umma::tc_fence_before();
@@ -955,26 +1043,38 @@ k_ray_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams prm
     umma::mbar_wait(bar, ph);
     ph ^= 1;
     umma::tc_fence_after();
-    // ---- R14: DensityMLP tail 32 -> 16 -> 1 in fp32
-    if (g == 0) {
+    // ---- R14: DensityMLP tail 32 -> 16 -> 1 in fp32, the 16 hidden units split over the column groups
+    {
       float h[32];
       umma::tmem_ld16(tlane + D_DEN, h);
       umma::tmem_ld16(tlane + D_DEN + 16, h + 16);
       umma::tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 32; ++i) h[i] = fmaxf(h[i] + prm.db0[i], 0.f);
-      float acc = prm.db4;
+      float part = 0.f;
 #pragma unroll
-      for (int o = 0; o < 16; ++o) {
-        float a = prm.db2[o];
+      for (int j = 0; j < 16 / G; ++j) {
+        const int o = g + G * j;
+        float a0 = prm.db2[o], a1 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) a = fmaf(h[i], prm.dw2[o][i], a);
-        acc = fmaf(fmaxf(a, 0.f), prm.dw4[o], acc);
+        for (int i = 0; i < 32; i += 2) {
+          a0 = fmaf(h[i], prm.dw2[o][i], a0);
+          a1 = fmaf(h[i + 1], prm.dw2[o][i + 1], a1);
+        }
+        part = fmaf(fmaxf(a0 + a1, 0.f), prm.dw4[o], part);
       }
-      if (row_ok) srdf[prow] = acc;
+      float* part_s = reinterpret_cast<float*>(smem + R_SCR);     // the split operands are dead (MMA completed)
+      part_s[g * 128 + r] = part;
+      umma::tc_fence_before();
+      __syncthreads();
+      if (g == 0 && row_ok) {
+        float acc = prm.db4;
+#pragma unroll
+        for (int j = 0; j < G; ++j) acc += part_s[j * 128 + r];
+        srdf[prow] = acc;
+      }
     }
-    umma::tc_fence_before();
-    __syncthreads();   // Q'/r_hi region and V' chunk 0.. are rewritten by the next tile's R2
+    __syncthreads();   // scratch / Q' / V' regions are rewritten by the next tile's R2
   }
   umma::tc_fence_before();
   __syncthreads();
