@@ -210,28 +210,73 @@ __device__ __forceinline__ void issue_gemm_sub(uint32_t tmem_d, uint32_t a_base,
 // identical values).  A pass over R*64 points with half = 0 | 1 addresses slot(p).
 __device__ __forceinline__ long long tc_slot(long long p, int half) { return (p >> 6) * kNS + half * kNC + (p & 63); }
 
+// Trilinear sample (align_corners=True, zeros) with one tap per lane: lane j of the 8-lane point group fetches the
+// whole 8-channel voxel of tap (dx,dy,dz) = (j&1, j>>1&1, j>>2), scales it by its tap weight, and a 3-step
+// reduce-scatter over the group leaves channel j of the interpolated feature in lane j (7 shuffles) and the
+// interpolated weight-volume value in every lane (3 shuffles).  Same taps and weights as tri_fetch, other summation order.
+__device__ __forceinline__ void tri_fetch_lane(const float* __restrict__ vf, const float* __restrict__ vw, int D, int H, int W,
+                                               float u, float v, float zn, int j, unsigned gmask, float& f_out, float& w_out) {
+  const float ix = gs_unnorm<true>(u, W), iy = gs_unnorm<true>(v, H), iz = gs_unnorm<true>(zn, D);
+  f_out = 0.f;
+  w_out = 0.f;
+  const bool near_vol = (ix > -1.f) && (ix < (float)W) && (iy > -1.f) && (iy < (float)H) && (iz > -1.f) && (iz < (float)D);
+  if (!near_vol) return;                               // uniform over the 8-lane group
+  const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+  const int dx = j & 1, dy = (j >> 1) & 1, dz = j >> 2;
+  const int x = (int)fx + dx, y = (int)fy + dy, z = (int)fz + dz;
+  const float wx = dx ? ix - fx : (fx + 1.f) - ix, wy = dy ? iy - fy : (fy + 1.f) - iy, wz = dz ? iz - fz : (fz + 1.f) - iz;
+  const bool ok = (x >= 0) && (x < W) && (y >= 0) && (y < H) && (z >= 0) && (z < D);
+  const float wgt = ok ? wx * wy * wz : 0.f;
+  const size_t idx = ok ? ((size_t)z * H + y) * W + x : 0;
+  float4 a = ldg4(vf + idx * kVolC), b = ldg4(vf + idx * kVolC + 4);
+  float ww = __ldg(vw + idx) * wgt;
+  a = f4_scale(a, wgt);
+  b = f4_scale(b, wgt);
+  const bool b2 = (j & 4) != 0, b1 = (j & 2) != 0, b0 = (j & 1) != 0;
+  float4 keep = b2 ? b : a;
+  const float4 send = b2 ? a : b;
+  keep.x += __shfl_xor_sync(gmask, send.x, 4);
+  keep.y += __shfl_xor_sync(gmask, send.y, 4);
+  keep.z += __shfl_xor_sync(gmask, send.z, 4);
+  keep.w += __shfl_xor_sync(gmask, send.w, 4);
+  float kx = b1 ? keep.z : keep.x, ky = b1 ? keep.w : keep.y;
+  const float sx = b1 ? keep.x : keep.z, sy = b1 ? keep.y : keep.w;
+  kx += __shfl_xor_sync(gmask, sx, 2);
+  ky += __shfl_xor_sync(gmask, sy, 2);
+  float k1 = b0 ? ky : kx;
+  const float s1 = b0 ? kx : ky;
+  k1 += __shfl_xor_sync(gmask, s1, 1);
+  ww += __shfl_xor_sync(gmask, ww, 4);
+  ww += __shfl_xor_sync(gmask, ww, 2);
+  ww += __shfl_xor_sync(gmask, ww, 1);
+  f_out = k1;
+  w_out = ww;
+}
+
 template <int NV, bool BF16>
-__global__ void __launch_bounds__(256) k_gather_tc(SceneDev sc, const float* __restrict__ rayinfo,
-                                                   const float* __restrict__ zbuf, int R, int half,
-                                                   const float* __restrict__ freqs, const float* __restrict__ phases,
-                                                   Mlp3Dev presim, uint16_t* __restrict__ tok, float4* __restrict__ rgbm,
-                                                   float4* __restrict__ dirs, float* __restrict__ sim8_out) {
+__global__ void __launch_bounds__(256, 3) k_gather_tc(SceneDev sc, const float* __restrict__ rayinfo,
+                                                      const float* __restrict__ zbuf, int R, int half,
+                                                      const float* __restrict__ freqs, const float* __restrict__ phases,
+                                                      Mlp3Dev presim, uint16_t* __restrict__ tok, float4* __restrict__ rgbm,
+                                                      float4* __restrict__ dirs, float* __restrict__ sim8_out) {
   constexpr int SN = kNC;
   __shared__ float s_sim[256][9];
-  __shared__ float s_w[8 * 32 + 32 + 32 * 32 + 32 + 32 * 16 + 16];
+  __shared__ __align__(16) float s_w[8 * 32 + 32 + 32 * 32 + 32 + 32 * 16 + 16];
+  constexpr int o_b0 = 8 * 32, o_w2 = o_b0 + 32, o_b2 = o_w2 + 32 * 32, o_w4 = o_b2 + 32, o_b4 = o_w4 + 32 * 16;
   {  // pre_sim_mlp weights -> shared memory
-    const int n0 = 8 * 32, n1 = 32, n2 = 32 * 32, n3 = 32, n4 = 32 * 16, n5 = 16;
-    for (int i = threadIdx.x; i < n0; i += 256) s_w[i] = __ldg(presim.w0 + i);
-    for (int i = threadIdx.x; i < n1; i += 256) s_w[n0 + i] = __ldg(presim.b0 + i);
-    for (int i = threadIdx.x; i < n2; i += 256) s_w[n0 + n1 + i] = __ldg(presim.w2 + i);
-    for (int i = threadIdx.x; i < n3; i += 256) s_w[n0 + n1 + n2 + i] = __ldg(presim.b2 + i);
-    for (int i = threadIdx.x; i < n4; i += 256) s_w[n0 + n1 + n2 + n3 + i] = __ldg(presim.w4 + i);
-    for (int i = threadIdx.x; i < n5; i += 256) s_w[n0 + n1 + n2 + n3 + n4 + i] = __ldg(presim.b4 + i);
+    for (int i = threadIdx.x; i < 8 * 32; i += 256) s_w[i] = __ldg(presim.w0 + i);
+    for (int i = threadIdx.x; i < 32; i += 256) s_w[o_b0 + i] = __ldg(presim.b0 + i);
+    for (int i = threadIdx.x; i < 32 * 32; i += 256) s_w[o_w2 + i] = __ldg(presim.w2 + i);
+    for (int i = threadIdx.x; i < 32; i += 256) s_w[o_b2 + i] = __ldg(presim.b2 + i);
+    for (int i = threadIdx.x; i < 32 * 16; i += 256) s_w[o_w4 + i] = __ldg(presim.w4 + i);
+    for (int i = threadIdx.x; i < 16; i += 256) s_w[o_b4 + i] = __ldg(presim.b4 + i);
   }
   const int sub = threadIdx.x >> 3, j = threadIdx.x & 7;
+  const unsigned gmask = 0xFFu << (threadIdx.x & 24);
   const long long P = (long long)R * SN;
   const long long p0 = (long long)blockIdx.x * 256;
   const float fj = __ldg(freqs + j), pj = __ldg(phases + j);
+  const size_t fstride = (size_t)sc.h * sc.w * kFeatC, istride = (size_t)sc.H * sc.W;
   for (int round = 0; round < 8; ++round) {
     const long long p = p0 + round * 32 + sub;
     if (p >= P) break;
@@ -241,64 +286,122 @@ __global__ void __launch_bounds__(256) k_gather_tc(SceneDev sc, const float* __r
     const float x = __fadd_rn(sc.ray_o[0], __fmul_rn(zz, ri[0]));
     const float y = __fadd_rn(sc.ray_o[1], __fmul_rn(zz, ri[1]));
     const float z = __fadd_rn(sc.ray_o[2], __fmul_rn(zz, ri[2]));
-    PointGather<NV> g;
-    gather_point<NV>(sc, x, y, z, j, fj, pj, g);
     const size_t sl = (size_t)tc_slot(p, half);
+    float u[NV], v[NV], qz[NV];
+#pragma unroll
+    for (int n = 0; n < NV; ++n) project_pt(sc.P[n], x, y, z, u[n], v[n], qz[n]);
+    // ---- frustum volumes first (their 24 values go to every view row): blended over views with the summed weights
+    float G[3] = {0.f, 0.f, 0.f}, Wsum = 0.f;
+    {
+      const float range = sc.far0 - sc.near0;
+#pragma unroll
+      for (int n = 0; n < NV; ++n) {
+        const float zn = ((qz[n] - sc.near0) / range) * 2.f - 1.f;       // camera.py:399-400
+        float f[3], wl = 0.f;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const size_t vox = (size_t)sc.vd[s] * sc.vh[s] * sc.vw[s];
+          float ws;
+          tri_fetch_lane(sc.vol_feat_cl[s] + n * vox * kVolC, sc.vol_w[s] + n * vox, sc.vd[s], sc.vh[s], sc.vw[s], u[n], v[n], zn,
+                         j, gmask, f[s], ws);
+          wl += ws;                                                        // model.py:375-378
+        }
+#pragma unroll
+        for (int s = 0; s < 3; ++s) G[s] = fmaf(f[s], wl, G[s]);           // model.py:381-386
+        Wsum += wl;
+      }
+      const float inv = 1.f / (Wsum + 1e-8f);                              // model.py:388
+#pragma unroll
+      for (int s = 0; s < 3; ++s) G[s] *= inv;
+    }
+    const uint16_t g0 = (uint16_t)(umma::pack2<BF16>(G[0], 0.f) & 0xffffu), g1 = (uint16_t)(umma::pack2<BF16>(G[1], 0.f) & 0xffffu),
+                   g2 = (uint16_t)(umma::pack2<BF16>(G[2], 0.f) & 0xffffu);
+    // ---- per view: feature, colour, MVS-depth gathers, depth PE, mask, relative direction -> token row (streamed out)
+    const float rx = x - sc.ref_o[0], ry = y - sc.ref_o[1], rz = z - sc.ref_o[2];
+    const float rn = 1.f / sqrtf(rx * rx + ry * ry + rz * rz);
 #pragma unroll
     for (int n = 0; n < NV; ++n) {
       uint16_t* row = tok + (sl * NV + n) * kDView;
+      const BilTaps tf = bil_setup<false, false>(u[n], v[n], sc.h, sc.w);
+      const float4 ft = bil_fetch32(sc.feat_cl + n * fstride, tf, j);
+      const BilTaps ti = bil_setup<false, false>(u[n], v[n], sc.H, sc.W);
+      const float4 c = bil_fetch_rgbd(sc.rgbd_cl + n * istride, ti);
+      const float zc = fmaf(sc.w2c_z[n][0], x, fmaf(sc.w2c_z[n][1], y, fmaf(sc.w2c_z[n][2], z, sc.w2c_z[n][3])));
+      const float pe = __sinf(fmaf(c.w - zc, fj, pj));                     // ray_transformer.py:66,245 (|arg| < ~40)
       uint2 f;
-      f.x = umma::pack2<BF16>(g.feat[n].x, g.feat[n].y);
-      f.y = umma::pack2<BF16>(g.feat[n].z, g.feat[n].w);
+      f.x = umma::pack2<BF16>(ft.x, ft.y);
+      f.y = umma::pack2<BF16>(ft.z, ft.w);
       *reinterpret_cast<uint2*>(row + 4 * j) = f;
-      row[32 + j] = (uint16_t)(umma::pack2<BF16>(g.vol[0], 0.f) & 0xffffu);
-      row[40 + j] = (uint16_t)(umma::pack2<BF16>(g.vol[1], 0.f) & 0xffffu);
-      row[48 + j] = (uint16_t)(umma::pack2<BF16>(g.vol[2], 0.f) & 0xffffu);
-      row[72 + j] = (uint16_t)(umma::pack2<BF16>(g.pe[n], 0.f) & 0xffffu);
+      row[32 + j] = g0;
+      row[40 + j] = g1;
+      row[48 + j] = g2;
+      row[72 + j] = (uint16_t)(umma::pack2<BF16>(pe, 0.f) & 0xffffu);
       if (j == 0) {
-        rgbm[sl * NV + n] = g.rgbm[n];
-        dirs[sl * NV + n] = g.dir[n];
+        const bool inb = (u[n] <= 1.f) && (u[n] >= -1.f) && (v[n] <= 1.f) && (v[n] >= -1.f);
+        rgbm[sl * NV + n] = make_float4(c.x, c.y, c.z, (inb && qz[n] > 0.f) ? 1.f : 0.f);
+        const float sx = x - sc.cam_o[n][0], sy = y - sc.cam_o[n][1], sz = z - sc.cam_o[n][2];
+        const float sn = 1.f / sqrtf(sx * sx + sy * sy + sz * sz);
+        dirs[sl * NV + n] = make_float4(rx * rn - sx * sn, ry * rn - sy * sn, rz * rn - sz * sn, 0.f);
       }
     }
-    s_sim[round * 32 + sub][j] = g.sim;
-    if (sim8_out != nullptr) sim8_out[sl * 8 + j] = g.sim;
+    // ---- pairwise similarity prior (one map per pair, stored in both views' slots)
+    {
+      float acc = 0.f;
+#pragma unroll
+      for (int a = 0; a < NV - 1; ++a)
+#pragma unroll
+        for (int b = a + 1; b < NV; ++b) {
+          const BilTaps ta = bil_setup<true, true>(u[a], v[a], sc.h, sc.w);
+          const BilTaps tb = bil_setup<true, true>(u[b], v[b], sc.h, sc.w);
+          const float4 fa = bil_fetch32(sc.match_cl + (size_t)(a * (NV - 1) + (b - 1)) * fstride, ta, j);
+          const float4 fb = bil_fetch32(sc.match_cl + (size_t)(b * (NV - 1) + a) * fstride, tb, j);
+          acc += cos4(fa, fb);
+        }
+      const float sim = acc / (float)(NV * (NV - 1) / 2);
+      s_sim[round * 32 + sub][j] = sim;
+      if (sim8_out != nullptr) sim8_out[sl * 8 + j] = sim;
+    }
   }
   __syncthreads();
   const long long p = p0 + threadIdx.x;
   if (p >= P) return;
-  // pre_sim_mlp 8 -> 32 -> 32 -> 16, one thread per point, weights broadcast from shared memory
-  const float* w0 = s_w;
-  const float* b0 = w0 + 8 * 32;
-  const float* w2 = b0 + 32;
-  const float* b2 = w2 + 32 * 32;
-  const float* w4 = b2 + 32;
-  const float* b4 = w4 + 32 * 16;
+  // pre_sim_mlp 8 -> 32 -> 32 -> 16, one thread per point, weight rows read as float4 broadcasts
   float s[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = s_sim[threadIdx.x][i];
   float h1[32];
 #pragma unroll
   for (int o = 0; o < 32; ++o) {
-    float a = b0[o];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) a = fmaf(s[i], w0[o * 8 + i], a);
-    h1[o] = fmaxf(a, 0.f);
+    const float4 wa = *reinterpret_cast<const float4*>(s_w + o * 8), wb = *reinterpret_cast<const float4*>(s_w + o * 8 + 4);
+    float a0 = fmaf(s[0], wa.x, s_w[o_b0 + o]), a1 = s[1] * wa.y;
+    a0 = fmaf(s[2], wa.z, a0); a1 = fmaf(s[3], wa.w, a1);
+    a0 = fmaf(s[4], wb.x, a0); a1 = fmaf(s[5], wb.y, a1);
+    a0 = fmaf(s[6], wb.z, a0); a1 = fmaf(s[7], wb.w, a1);
+    h1[o] = fmaxf(a0 + a1, 0.f);
   }
   float h2[32];
 #pragma unroll
   for (int o = 0; o < 32; ++o) {
-    float a = b2[o];
+    float a0 = s_w[o_b2 + o], a1 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) a = fmaf(h1[i], w2[o * 32 + i], a);
-    h2[o] = fmaxf(a, 0.f);
+    for (int i = 0; i < 32; i += 4) {
+      const float4 w = *reinterpret_cast<const float4*>(s_w + o_w2 + o * 32 + i);
+      a0 = fmaf(h1[i], w.x, a0); a1 = fmaf(h1[i + 1], w.y, a1);
+      a0 = fmaf(h1[i + 2], w.z, a0); a1 = fmaf(h1[i + 3], w.w, a1);
+    }
+    h2[o] = fmaxf(a0 + a1, 0.f);
   }
   float o16[16];
 #pragma unroll
   for (int o = 0; o < 16; ++o) {
-    float a = b4[o];
+    float a0 = s_w[o_b4 + o], a1 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) a = fmaf(h2[i], w4[o * 32 + i], a);
-    o16[o] = a;
+    for (int i = 0; i < 32; i += 4) {
+      const float4 w = *reinterpret_cast<const float4*>(s_w + o_w4 + o * 32 + i);
+      a0 = fmaf(h2[i], w.x, a0); a1 = fmaf(h2[i + 1], w.y, a1);
+      a0 = fmaf(h2[i + 2], w.z, a0); a1 = fmaf(h2[i + 3], w.w, a1);
+    }
+    o16[o] = a0 + a1;
   }
   const uint4 lo = tc::pack8<BF16>(o16), hi = tc::pack8<BF16>(o16 + 8);
   const size_t sl = (size_t)tc_slot(p, half);
