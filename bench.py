@@ -220,6 +220,7 @@ def workload_config(args, views, ckpt_src, mode_name):
             "rays_per_depth_map": args.width * args.height, "n_views": args.nv, "mode": mode_name,
             "checkpoint": ckpt_src,
             "l2": "inputs larger than L2 (scene tensors 4.2 GB at 1600x1216 vs 126 MB L2); no explicit flush",
+            "timing": "value/ms_per_step: K steps between CUDA events, no per-kernel brackets; roofline: the same K steps repeated with every launch bracketed by CUDA events",
             "parallelism": f"dp{args.gpus} (one full depth map per rank per step; no collective in the timed region)"}
 
 
@@ -298,12 +299,11 @@ def run_b200(args):
         step_resident()
     barrier()
 
-    # ---- timed region: K steps, CUDA events on the launching stream, per-kernel event brackets on
+    # ---- timed region: K steps, CUDA events on the launching stream
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
     launches0 = lib.ufo_launch_count()
-    _lib.profile_begin()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -312,11 +312,21 @@ def run_b200(args):
     e1.record(stream)
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    prof = _lib.profile_end(256)
     launches = lib.ufo_launch_count() - launches0
-    clk = clocks.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     value = world * n_rays * args.steps / (ms_total * 1e-3)
+    # ---- the same K steps again with every launch bracketed by CUDA events (ufo_profile_*): per-kernel device time
+    #      for the roofline entries; kept out of the region above because the 2 event records per launch cost ~3 %
+    _lib.profile_begin()
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+    e1.record(stream)
+    barrier()
+    ms_prof_total = max_over_ranks(e0.elapsed_time(e1))
+    prof = _lib.profile_end(256)
+    clk = clocks.stop() if rank == 0 else None
 
     # ---- e2e: host buffers, copies inside the timed region
     for _ in range(1):
@@ -349,7 +359,14 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel
     pk = peaks()
-    roof = roofline_from_profile(prof, args, n_rays, pk)
+    roofs = roofline_entries(prof, args, n_rays, pk)
+    roof = roofs[0] if roofs else None
+    costvol = None
+    if rank == 0 and world == 1 and not args.no_costvolume:
+        try:
+            costvol = bench_costvolume(args, dev)
+        except Exception as ex:  # measurement extra: never fail the headline line
+            costvol = {"error": str(ex)}
 
     # ---- CPU baseline (rank 0, N=1 only)
     cpu = None
@@ -375,6 +392,9 @@ def run_b200(args):
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": roof,
+            "rooflines": roofs,
+            "costvolume": costvol,
+            "profiled_ms_per_step": ms_prof_total / args.steps,
             "kernels": [{"name": n, "launches": c, "ms": round(ms, 3)} for n, c, ms in sorted(prof, key=lambda x: -x[2])[:12]],
             "cpu_baseline": cpu,
             "setup_s": round(setup_s, 1),
@@ -387,43 +407,91 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def roofline_from_profile(prof, args, n_rays, pk):
-    """Roofline entry of the kernel with the largest share of the timed region."""
+def _ncu_traffic():
+    """dram bytes per launch from the committed ncu --set full capture (profiles/ncu_traffic.json), or {}."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
+def roofline_entries(prof, args, n_rays, pk):
+    """One roofline entry per kernel family of the timed region, largest share first."""
     if not prof:
-        return None
+        return []
     total_ms = sum(ms for _, _, ms in prof)
-    name, cnt, ms = max(prof, key=lambda x: x[2])
     nv = args.nv
     fl = flops_per_point(nv)
-    pts = n_rays * 192 * args.steps           # sample-point evaluations in the timed region (64 coarse + 128 fine)
-    avg_s = ms * 1e-3 / cnt
-    work = None
-    bound, unit = "tensor", "TFLOP/s"
-    if name.startswith("k_view_tc"):
-        work = pts * (fl["view"] + fl["radiance"])
-    elif name.startswith("k_ray_tc"):
-        work = pts * (fl["ray"] + fl["density"])
-    elif name.startswith("k_linear<"):
-        k, n = [int(x) for x in name[len("k_linear<"):-1].split(",")]
-        rows = {80: pts * (nv + 1), 160: pts * (nv + 1), 88: pts, 176: pts}[k]
-        work = 2.0 * rows * k * n
-    elif name.startswith("k_gather"):
-        bound, unit = "hbm", "GB/s"
-        work = pts * tap_bytes_per_point(nv)
-    if work is None:
-        return {"kernel": name, "share_of_step": ms / total_ms, "bound": None, "achieved": None, "peak": None,
-                "unit": None, "frac": None, "traffic": None}
-    per_launch = work / cnt
-    if bound == "tensor":
-        achieved = per_launch / avg_s / 1e12
-        peak = pk["tf_sustained"]
-    else:
-        achieved = per_launch / avg_s / 1e9
-        peak = pk["hbm_gbs"]
-    return {"kernel": name, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
-            "traffic": None, "peak_source": pk["src"] + (" (sustained bf16)" if bound == "tensor" else " (copy)"),
-            "launches": cnt, "avg_launch_ms": avg_s * 1e3, "share_of_step": ms / total_ms,
-            "algorithmic_work_per_launch": per_launch}
+    pts = n_rays * 192 * args.steps           # the reference's sample-point evaluations per ray: 64 coarse + 128 fine
+    traffic = _ncu_traffic()
+    out = []
+    for name, cnt, ms in sorted(prof, key=lambda x: -x[2]):
+        bound, unit, work, note = "tensor", "TFLOP/s", None, None
+        if name.startswith("k_view_tc"):
+            work = pts * (fl["view"] + fl["radiance"])
+        elif name.startswith("k_ray_tc"):
+            work = pts * (fl["ray"] + fl["density"])
+        elif name.startswith("k_linear<"):
+            k, n = [int(x) for x in name[len("k_linear<"):-1].split(",")]
+            rows = {80: pts * (nv + 1), 160: pts * (nv + 1), 88: pts, 176: pts}[k]
+            work = 2.0 * rows * k * n
+        elif name.startswith("k_gather"):
+            bound, unit = "hbm", "GB/s"
+            work = pts * tap_bytes_per_point(nv)
+            note = "algorithmic bytes = texel/voxel tap bytes (L1/L2 level); compulsory HBM bytes are the 4.2 GB scene"
+        if work is None:
+            continue
+        avg_s = ms * 1e-3 / cnt
+        per_launch = work / cnt
+        achieved = per_launch / avg_s / (1e12 if bound == "tensor" else 1e9)
+        peak = pk["tf_sustained"] if bound == "tensor" else pk["hbm_gbs"]
+        e = {"kernel": name, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
+             "traffic": traffic.get(name.split("<")[0]),
+             "peak_source": pk["src"] + (" (sustained bf16)" if bound == "tensor" else " (copy)"),
+             "launches": cnt, "avg_launch_ms": avg_s * 1e3, "share_of_step": ms / total_ms,
+             "algorithmic_work_per_launch": per_launch,
+             "work_basis": "reference evaluation count: 192 sample points per ray (the path skips the 64 redundant "
+                           "re-evaluations of the fine pass in the gather and view stages)"}
+        if note:
+            e["note"] = note
+        out.append(e)
+    return out
+
+
+def bench_costvolume(args, dev):
+    """Kernel 1 (cost-volume build, TransMVSNet.py:76-100) at the workload's size: 3 cascade stages, N = V = n_views."""
+    from uforecon_b200 import _lib, checkpoint
+    from uforecon_b200.costvolume import similarity_volume
+    from uforecon_b200 import synthetic
+    nv, W, H = args.nv, args.width, args.height
+    sd = checkpoint.synthetic_state_dict(0)
+    batch = synthetic.make_batch(view_ids(args.views, nv), (W, H))
+    comb = [list(range(i, nv)) + list(range(0, i)) for i in range(nv)]
+    g = torch.Generator(device=dev).manual_seed(3)
+    res = []
+    vw = None
+    for si, (stage, D, C) in enumerate((("stage1", 48, 32), ("stage2", 32, 16), ("stage3", 8, 8))):
+        sc = synthetic.STAGE_SCALE[stage]
+        hs, ws = H // sc, W // sc
+        feats = [torch.randn(nv, C, hs, ws, device=dev, generator=g) for _ in range(nv)]
+        proj = batch["proj_matrices"][stage][0][comb].contiguous()
+        base = 425.0 + 2.65 * 192 * (0.3 + 0.4 * torch.rand(nv, 1, hs, ws, device=dev, generator=g))
+        hyp = (base + (torch.arange(D, device=dev).view(1, D, 1, 1) - D / 2) * 2.65 * (4 / (si + 1)) * (4.0 if si == 0 else 1.0)).contiguous()
+        if vw is not None:
+            vw = torch.nn.functional.interpolate(vw, scale_factor=2, mode="nearest").contiguous()
+        similarity_volume(feats, proj, hyp, sd, view_weights=vw, device=dev)          # warm-up
+        _lib.profile_begin()
+        for _ in range(3):
+            sim, vw_new = similarity_volume(feats, proj, hyp, sd, view_weights=vw, device=dev)
+        prof = _lib.profile_end(64)
+        ms = sum(m for n, c, m in prof if n.startswith("k_costvol")) / 3
+        ms_repack = sum(m for n, c, m in prof if n.startswith("k_nchw")) / 3
+        vox = nv * D * hs * ws
+        tap = vox * (nv - 1) * (4 * C * 4 + C * 4 / (nv - 1)) + vox * 4
+        compulsory = nv * nv * C * hs * ws * 4 + vox * 4 * 2
+        res.append({"stage": stage, "voxels": vox, "kernel_ms": ms, "repack_ms": ms_repack,
+                    "tap_gbs": tap / (ms * 1e-3) / 1e9, "compulsory_gbs": compulsory / (ms * 1e-3) / 1e9})
+        vw = vw_new
+        del feats, sim
+    return res
 
 
 def main():
@@ -432,7 +500,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("UFO_BENCH_MODE", "fp32"), choices=["fp32", "tc", "tc16"])
+    ap.add_argument("--mode", default=os.environ.get("UFO_BENCH_MODE", "tc"), choices=["fp32", "tc", "tc16"])
     ap.add_argument("--width", type=int, default=int(os.environ.get("UFO_BENCH_W", "1600")))
     ap.add_argument("--height", type=int, default=int(os.environ.get("UFO_BENCH_H", "1216")))
     ap.add_argument("--nv", type=int, default=3)
@@ -441,6 +509,7 @@ def main():
     ap.add_argument("--cpu-chunks", type=int, default=4)
     ap.add_argument("--ref-chunks", type=int, default=2, help="--impl reference: 800-ray chunks per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-costvolume", action="store_true")
     ap.add_argument("--rays", type=int, default=0, help="profiling aid: render only the first N rays of the map per step")
     args = ap.parse_args()
     if args.impl == "reference":

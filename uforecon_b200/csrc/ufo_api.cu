@@ -131,10 +131,15 @@ static int tc_weights_build(const UfoWeightsDesc* d, TcWeights* t, cudaStream_t 
       pack_b(vi.data() + tc::V_WMRG, d->view.merge, 80, 80, 80, 80, 80, bf16);
       pack_b(vi.data() + tc::V_WML0, d->view.mlp0, 160, 160, 160, 160, 160, bf16);
       pack_b(vi.data() + tc::V_WML2, d->view.mlp2, 80, 160, 160, 80, 160, bf16);
-      std::vector<float> rad((size_t)16 * 160);   // [W0x | W0x]: the head sees x + LN2 without forming the sum
-      for (int o = 0; o < 16; ++o)
-        for (int k = 0; k < 80; ++k) rad[o * 160 + k] = rad[o * 160 + 80 + k] = d->radiance.w0[o * 83 + k];
-      pack_b(vi.data() + tc::V_WRAD, rad.data(), 16, 160, 160, 16, 160, bf16);
+      // [W0x | W0x | W0dir b0 0..]: the head sees x + LN2 without forming the sum; direction and bias ride in two
+      // extra K chunks of the operand (columns 160..162 = relative direction, 163 = 1)
+      std::vector<float> rad((size_t)16 * 176, 0.f);
+      for (int o = 0; o < 16; ++o) {
+        for (int k = 0; k < 80; ++k) rad[o * 176 + k] = rad[o * 176 + 80 + k] = d->radiance.w0[o * 83 + k];
+        for (int k = 0; k < 3; ++k) rad[o * 176 + 160 + k] = d->radiance.w0[o * 83 + 80 + k];
+        rad[o * 176 + 163] = d->radiance.b0[o];
+      }
+      pack_b(vi.data() + tc::V_WRAD, rad.data(), 16, 176, 176, 16, 176, bf16);
     }
     {  // ray stage
       std::vector<float> qkv((size_t)264 * 88);
@@ -537,7 +542,7 @@ static int render_chunk_fp32(const UfoScene* sc, const UfoWeights* w, const int6
 // ------------------------------------------------------------------------------------------------
 static int tc_chunk_rays(int sms) {
   const char* e = getenv("UFO_TC_CHUNK");
-  int v = e ? atoi(e) : sms * 8;    // fine pass: 8 ray tiles per CTA; view stage: 32 point tiles per CTA (NV = 3)
+  int v = e ? atoi(e) : sms * 64;   // fine pass: 64 ray tiles per CTA; fewer launches and weight reloads per ray
   return v < 2 ? 2 : v;
 }
 

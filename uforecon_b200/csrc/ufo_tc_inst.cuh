@@ -25,7 +25,7 @@ static int launch_tc_pass(const UfoScene* sc, const UfoWeights* w, int R, int ha
     constexpr int PPT = 128 / (NV + 1);
     const long long tiles = (P + PPT - 1) / PPT;
     const int grid = (int)(tiles < sms ? tiles : sms);
-    UFO_KERNEL("k_view_tc", st, k_view_tc<NV, BF16><<<grid, tc::kThreads, tc::V_SMEM, st>>>(w->tc.view_img[f], w->tc.vp, ws.tok, ws.rgbm, ws.dirs, P, half,
+    UFO_KERNEL("k_view_tc", st, k_view_tc<NV, BF16><<<grid, tc::kThreads, tc::V_SMEM, st>>>(w->tc.view_img[f], w->tc.vp, ws.tok, ws.rgbm, ws.dirs, (int)P, half,
                                                                                            ws.vout0, ws.radiance));
   }
   if (half == 0) {

@@ -23,11 +23,12 @@ constexpr uint32_t V_WQKV = 0;                      // [240][80]
 constexpr uint32_t V_WMRG = V_WQKV + 240 * 80 * 2;  // [80][80]
 constexpr uint32_t V_WML0 = V_WMRG + 80 * 80 * 2;   // [160][160]
 constexpr uint32_t V_WML2 = V_WML0 + 160 * 160 * 2; // [80][160]
-constexpr uint32_t V_WRAD = V_WML2 + 80 * 160 * 2;  // [16][160]  = [W0x | W0x]
-constexpr uint32_t V_WEND = V_WRAD + 16 * 160 * 2;  // 133120
+constexpr uint32_t V_WRAD = V_WML2 + 80 * 160 * 2;  // [16][176]  = [W0x | W0x | W0dir(3) b0 0..]
+constexpr uint32_t V_WEND = V_WRAD + 16 * 176 * 2;  // 133632
 constexpr uint32_t V_X = V_WEND;                    // chunks 0..9   (token)
 constexpr uint32_t V_M = V_X + 10 * kChunk;         // chunks 10..19 (message / LN1 / LN2 output)
-constexpr uint32_t V_KV = V_M + 10 * kChunk;        // K',V' staging [8 heads][128][40 B]; later H1 (20 chunks)
+constexpr uint32_t V_E = V_M + 10 * kChunk;         // chunks 20..21 (relative direction, 1, 0...) for the radiance head
+constexpr uint32_t V_KV = V_E + 2 * kChunk;         // K',V' staging [8 heads][128][40 B]; later H1 (20 chunks)
 constexpr uint32_t V_RED = V_KV + 20 * kChunk;      // float2 [kGroups][128]  LayerNorm partials
 constexpr uint32_t V_OMG = V_RED + 8 * kGroups * 128;  // float [kGroups][128]   radiance-head partials
 constexpr uint32_t V_BAR = V_OMG + 4 * kGroups * 128;

@@ -161,14 +161,11 @@ __device__ __forceinline__ void ln_apply(const float2* v, float2 st, const float
   }
 }
 
-// split a float into a 16-bit head and the 16-bit remainder (hi + lo ~ x to ~2^-17 / 2^-22 relative)
+// split a float into a head that is exactly representable in the 16-bit operand format (mantissa truncated to
+// 8 / 11 bits; assumes |x| inside the fp16 range in fp16 mode) and the exact remainder: hi + lo == x
 template <bool BF16>
 __device__ __forceinline__ void split_hi_lo(float x, float& hi, float& lo) {
-  if (BF16) {
-    hi = __bfloat162float(__float2bfloat16_rn(x));
-  } else {
-    hi = __half2float(__float2half_rn(x));
-  }
+  hi = __uint_as_float(__float_as_uint(x) & (BF16 ? 0xffff0000u : 0xffffe000u));
   lo = x - hi;
 }
 
@@ -419,7 +416,7 @@ __global__ void __launch_bounds__(256, 3) k_gather_tc(SceneDev sc, const float* 
 template <int NV, bool BF16>
 __global__ void __launch_bounds__(tc::kThreads, 1)
 k_view_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams prm, const uint16_t* __restrict__ tok,
-          const float4* __restrict__ rgbm, const float4* __restrict__ dirs, long long P, int half,
+          const float4* __restrict__ rgbm, const float4* __restrict__ dirs, int P, int half,
           float* __restrict__ vout0, float4* __restrict__ radiance) {
   using namespace tc;
   static_assert(kGroups == 4, "epilogues are written for 4 column groups (2 heads per thread)");
@@ -446,7 +443,7 @@ k_view_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams p
   for (uint32_t i = tid; i < V_WEND / 16; i += kThreads)
     reinterpret_cast<uint4*>(smem)[i] = __ldg(reinterpret_cast<const uint4*>(wimg) + i);
   // token rows: row l == 0 of every point is the learnable view token (constant), pad rows are zero
-  for (int i = tid; i < 128 * 20; i += kThreads) {
+  for (int i = tid; i < 128 * 22; i += kThreads) {
     const int rr = i & 127, c = i >> 7;
     float v[8];
 #pragma unroll
@@ -461,7 +458,7 @@ k_view_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams p
   const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
   const uint32_t sm_base = umma::smem_u32(smem);
   uint32_t ph = 0;
-  const long long n_tiles = (P + PPT - 1) / PPT;
+  const int n_tiles = (P + PPT - 1) / PPT;
 
   // 16-byte pieces of the token rows, prefetched one tile ahead into registers; the (row, chunk) -> (point, view)
   // mapping of a piece does not depend on the tile
@@ -478,26 +475,27 @@ k_view_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams p
     pf_off[k] = (ll - 1) * kDView + c * 8;
     pf_dst[k] = (uint32_t)(c * kChunk + rr * 16);
   }
-  auto prefetch = [&](long long tile) {
-    const long long pbase = tile * PPT;
+  auto slot_of = [&](int p) -> int { return (p >> 6) * kNS + half * kNC + (p & 63); };
+  auto prefetch = [&](int tile) {
+    const int pbase = tile * PPT;
 #pragma unroll
     for (int k = 0; k < NPF; ++k) {
       pf[k] = make_uint4(0, 0, 0, 0);
-      const long long p = pbase + pf_pt[k];
+      const int p = pbase + pf_pt[k];
       if (pf_pt[k] >= 0 && tile < n_tiles && p < P)
-        pf[k] = __ldg(reinterpret_cast<const uint4*>(tok + (size_t)tc_slot(p, half) * (NV * kDView) + pf_off[k]));
+        pf[k] = __ldg(reinterpret_cast<const uint4*>(tok + (size_t)slot_of(p) * (NV * kDView) + pf_off[k]));
     }
   };
   prefetch(blockIdx.x);
 
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const long long pbase = tile * PPT;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int pbase = tile * PPT;
     // ---- P0: token rows of this tile (prefetched) -> X (A operand, K = 80)
 #pragma unroll
     for (int k = 0; k < NPF; ++k)
       if (pf_pt[k] >= 0) *reinterpret_cast<uint4*>(smem + V_X + pf_dst[k]) = pf[k];
-    const long long my_p = pbase + pl;
-    const size_t my_slot = (size_t)tc_slot(my_p, half);
+    const int my_p = pbase + pl;
+    const size_t my_slot = (size_t)slot_of(my_p);
     const bool view_row = row_ok && l > 0 && my_p < P;
     umma::fence_async_smem();
     umma::tc_fence_before();
@@ -692,14 +690,18 @@ k_view_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams p
         }
       };
       UFO_G_DISPATCH(ln2)
+      if (g == 0) {   // radiance-head side inputs of this row: relative direction and the constant 1 that carries the bias
+        const float e[8] = {my_dir.x, my_dir.y, my_dir.z, 1.f, 0.f, 0.f, 0.f, 0.f};
+        st_chunk<BF16>(smem + V_M, r, 10, e);
+      }
     }
     umma::fence_async_smem();
     umma::tc_fence_before();
     __syncthreads();
-    // ---- P10: LN2 half of the radiance head's first layer        (ray_transformer.py:159-163,313)
+    // ---- P10: LN2 half of the radiance head's first layer + direction/bias chunks   (ray_transformer.py:159-163,313)
     if (tid == 0) {
       umma::tc_fence_after();
-      issue_gemm_sub(tmem + D_RAD, sm_base + V_M, sm_base + V_WRAD + 10 * (16 * 16), 16, 0, 10, umma::make_idesc(128, 16, FMT, false, false), 1);
+      issue_gemm_sub(tmem + D_RAD, sm_base + V_M, sm_base + V_WRAD + 10 * (16 * 16), 16, 0, 12, umma::make_idesc(128, 16, FMT, false, false), 1);
       umma::commit(bar);
     }
     umma::mbar_wait(bar, ph);
@@ -713,8 +715,7 @@ k_view_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams p
       auto tail = [&](auto GGc) {
         constexpr int GG = decltype(GGc)::value;
 #pragma unroll
-        for (int o = 0; o < 16; ++o)
-          h[o] = fmaxf(h[o] + prm.rb0[o] + prm.rw0d[o][0] * my_dir.x + prm.rw0d[o][1] * my_dir.y + prm.rw0d[o][2] * my_dir.z, 0.f);
+        for (int o = 0; o < 16; ++o) h[o] = fmaxf(h[o], 0.f);      // bias and direction terms came through the GEMM
         float part = 0.f;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -736,7 +737,7 @@ k_view_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams p
     umma::tc_fence_before();
     __syncthreads();
     if (tid < PPT && pbase + tid < P) {
-      const size_t p = (size_t)tc_slot(pbase + tid, half);
+      const size_t p = (size_t)slot_of(pbase + tid);
       float om[NV];
       float4 col[NV];
       float mx = -INFINITY;
@@ -1146,36 +1147,35 @@ k_ray_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams prm
     umma::mbar_wait(bar, ph);
     ph ^= 1;
     umma::tc_fence_after();
-    // ---- R14: DensityMLP tail 32 -> 16 -> 1 in fp32, the 16 hidden units split over the column groups
+    // ---- R14: DensityMLP tail 32 -> 16 -> 1 in fp32, hidden units g, g+4, g+8, g+12 per thread
     {
       float h[32];
       umma::tmem_ld16(tlane + D_DEN, h);
       umma::tmem_ld16(tlane + D_DEN + 16, h + 16);
       umma::tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) h[i] = fmaxf(h[i] + prm.db0[i], 0.f);
-      float part = 0.f;
-#pragma unroll
-      for (int j = 0; j < 16 / G; ++j) {
-        const int o = g + G * j;
-        float a0 = prm.db2[o], a1 = 0.f;
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          a0 = fmaf(h[i], prm.dw2[o][i], a0);
-          a1 = fmaf(h[i + 1], prm.dw2[o][i + 1], a1);
-        }
-        part = fmaf(fmaxf(a0 + a1, 0.f), prm.dw4[o], part);
-      }
       float* part_s = reinterpret_cast<float*>(smem + R_SCR);     // the split operands are dead (MMA completed)
-      part_s[g * 128 + r] = part;
+      auto tail = [&](auto GGc) {
+        constexpr int GG = decltype(GGc)::value;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) h[i] = fmaxf(h[i] + prm.db0[i], 0.f);
+        float part = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          constexpr int dummy = 0;
+          (void)dummy;
+          const int o = GG + 4 * j;
+          float2 acc = make_float2(prm.db2[o], 0.f);
+#pragma unroll
+          for (int i = 0; i < 32; i += 2)
+            acc = __ffma2_rn(make_float2(h[i], h[i + 1]), make_float2(prm.dw2[o][i], prm.dw2[o][i + 1]), acc);
+          part = fmaf(fmaxf(acc.x + acc.y, 0.f), prm.dw4[o], part);
+        }
+        part_s[GG * 128 + r] = part;
+      };
+      UFO_G_DISPATCH(tail)
       umma::tc_fence_before();
       __syncthreads();
-      if (g == 0 && row_ok) {
-        float acc = prm.db4;
-#pragma unroll
-        for (int j = 0; j < G; ++j) acc += part_s[j * 128 + r];
-        srdf[prow] = acc;
-      }
+      if (g == 0 && row_ok) srdf[prow] = prm.db4 + ((part_s[r] + part_s[128 + r]) + (part_s[256 + r] + part_s[384 + r]));
     }
     __syncthreads();   // scratch / Q' / V' regions are rewritten by the next tile's R2
   }
