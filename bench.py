@@ -420,13 +420,17 @@ def roofline_entries(prof, args, n_rays, pk):
     total_ms = sum(ms for _, _, ms in prof)
     nv = args.nv
     fl = flops_per_point(nv)
-    pts = n_rays * 192 * args.steps           # the reference's sample-point evaluations per ray: 64 coarse + 128 fine
+    # sample points a launch really processes: the ray stage sees 64 + 128 per ray like the reference; the gathers and
+    # the view stage see 64 + 64 in the tensor-core modes (coarse results are reused) and 64 + 128 in fp32 mode
+    pts_ray = n_rays * 192 * args.steps
+    pts_pt = n_rays * (128 if args.mode != "fp32" else 192) * args.steps
+    pts = pts_ray
     traffic = _ncu_traffic()
     out = []
     for name, cnt, ms in sorted(prof, key=lambda x: -x[2]):
         bound, unit, work, note = "tensor", "TFLOP/s", None, None
         if name.startswith("k_view_tc"):
-            work = pts * (fl["view"] + fl["radiance"])
+            work = pts_pt * (fl["view"] + fl["radiance"])
         elif name.startswith("k_ray_tc"):
             work = pts * (fl["ray"] + fl["density"])
         elif name.startswith("k_linear<"):
@@ -435,7 +439,7 @@ def roofline_entries(prof, args, n_rays, pk):
             work = 2.0 * rows * k * n
         elif name.startswith("k_gather"):
             bound, unit = "hbm", "GB/s"
-            work = pts * tap_bytes_per_point(nv)
+            work = pts_pt * tap_bytes_per_point(nv)
             note = "algorithmic bytes = texel/voxel tap bytes (L1/L2 level); compulsory HBM bytes are the 4.2 GB scene"
         if work is None:
             continue
@@ -448,8 +452,9 @@ def roofline_entries(prof, args, n_rays, pk):
              "peak_source": pk["src"] + (" (sustained bf16)" if bound == "tensor" else " (copy)"),
              "launches": cnt, "avg_launch_ms": avg_s * 1e3, "share_of_step": ms / total_ms,
              "algorithmic_work_per_launch": per_launch,
-             "work_basis": "reference evaluation count: 192 sample points per ray (the path skips the 64 redundant "
-                           "re-evaluations of the fine pass in the gather and view stages)"}
+             "work_basis": "algorithmic work of the sample points the launches process (ray stage 192 per ray; gathers and "
+                           "view stage 128 per ray in the tensor-core modes, where the fine pass reuses the coarse results; "
+                           "the reference evaluates 192)"}
         if note:
             e["note"] = note
         out.append(e)
@@ -472,7 +477,7 @@ def bench_costvolume(args, dev):
         sc = synthetic.STAGE_SCALE[stage]
         hs, ws = H // sc, W // sc
         feats = [torch.randn(nv, C, hs, ws, device=dev, generator=g) for _ in range(nv)]
-        proj = batch["proj_matrices"][stage][0][comb].contiguous()
+        proj = batch["proj_matrices"][stage][0][torch.tensor(comb)].contiguous()
         base = 425.0 + 2.65 * 192 * (0.3 + 0.4 * torch.rand(nv, 1, hs, ws, device=dev, generator=g))
         hyp = (base + (torch.arange(D, device=dev).view(1, D, 1, 1) - D / 2) * 2.65 * (4 / (si + 1)) * (4.0 if si == 0 else 1.0)).contiguous()
         if vw is not None:
