@@ -14,7 +14,14 @@ static int launch_tc_pass(const UfoScene* sc, const UfoWeights* w, int R, int ha
   const TcWorkspace& ws = sc->tws;
   const long long P = (long long)R * kNC;
   const int f = BF16 ? 0 : 1;
-  UFO_KERNEL("k_gather_tc", st, k_gather_tc<NV, BF16><<<cdiv(P, 256), 256, 0, st>>>(sc->d, ws.rayinfo, z, R, half, w->freqs, w->phases, w->pre_sim,
+  {
+    static bool attr = false;
+    if (!attr) {
+      UFO_CUDA(cudaFuncSetAttribute(k_gather_tc<NV, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gather_tc_smem<NV>()));
+      attr = true;
+    }
+  }
+  UFO_KERNEL("k_gather_tc", st, k_gather_tc<NV, BF16><<<cdiv(P, 256), 256, gather_tc_smem<NV>(), st>>>(sc->d, ws.rayinfo, z, R, half, w->freqs, w->phases, w->pre_sim,
                                                                                   ws.tok, ws.rgbm, ws.dirs, want_sim8 ? ws.sim8 : nullptr));
   {
     static bool attr = false;

@@ -250,6 +250,40 @@ __device__ __forceinline__ void tri_fetch_lane(const float* __restrict__ vf, con
   w_out = ww;
 }
 
+// bil_setup with the grid_sample convention as run-time flags (one code path for the three gather flavours)
+__device__ __forceinline__ BilTaps bil_setup_rt(float u, float v, int H, int W, bool align, bool border) {
+  float ix = align ? ((u + 1.f) / 2.f) * (float)(W - 1) : ((u + 1.f) * (float)W - 1.f) / 2.f;
+  float iy = align ? ((v + 1.f) / 2.f) * (float)(H - 1) : ((v + 1.f) * (float)H - 1.f) / 2.f;
+  if (border) {
+    ix = fminf(fmaxf(ix, 0.f), (float)(W - 1));
+    iy = fminf(fmaxf(iy, 0.f), (float)(H - 1));
+  }
+  BilTaps t;
+  const bool near_img = (ix > -1.f) && (ix < (float)W) && (iy > -1.f) && (iy < (float)H);  // false for NaN/inf
+  const float fx = floorf(ix), fy = floorf(iy);
+  const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+  const float wx1 = ix - fx, wx0 = (fx + 1.f) - ix, wy1 = iy - fy, wy0 = (fy + 1.f) - iy;
+  const bool vx0 = near_img && x0 >= 0, vx1 = near_img && x1 < W, vy0 = y0 >= 0, vy1 = y1 < H;
+  const int cx0 = min(max(x0, 0), W - 1), cx1 = min(max(x1, 0), W - 1), cy0 = min(max(y0, 0), H - 1), cy1 = min(max(y1, 0), H - 1);
+  t.i00 = near_img ? cy0 * W + cx0 : 0; t.i01 = near_img ? cy0 * W + cx1 : 0;
+  t.i10 = near_img ? cy1 * W + cx0 : 0; t.i11 = near_img ? cy1 * W + cx1 : 0;
+  t.w00 = (vx0 && vy0) ? wx0 * wy0 : 0.f;
+  t.w01 = (vx1 && vy0) ? wx1 * wy0 : 0.f;
+  t.w10 = (vx0 && vy1) ? wx0 * wy1 : 0.f;
+  t.w11 = (vx1 && vy1) ? wx1 * wy1 : 0.f;
+  return t;
+}
+
+// shared-memory bytes of k_gather_tc<NV>: pre_sim_mlp weights, similarity staging, per-round projections and taps
+constexpr int kGatherWFloats = 8 * 32 + 32 + 32 * 32 + 32 + 32 * 16 + 16 + 16;   // + pad to a 16-byte multiple
+template <int NV>
+constexpr int gather_tc_smem() { return kGatherWFloats * 4 + 256 * 9 * 4 + 32 * NV * 16 + 32 * 3 * NV * 32; }
+
+// Per round of 32 points the 8 lanes of a point group SHARE the per-view work that does not depend on the channel:
+// lane j projects the point into view k%NV and sets up the bilinear taps of flavour k/NV (0: features, align_corners
+// False / zeros on h x w; 1: colour+depth, same on H x W; 2: match maps, align_corners True / border on h x w) for
+// k = j, j+8, ..; results go through shared memory.  (The exact path k_gather recomputes them in every lane and,
+// for the match maps, for every pair: 3 NV + NV(NV-1) set-ups per lane instead of ceil(3 NV / 8).)
 template <int NV, bool BF16>
 __global__ void __launch_bounds__(256, 3) k_gather_tc(SceneDev sc, const float* __restrict__ rayinfo,
                                                       const float* __restrict__ zbuf, int R, int half,
@@ -257,8 +291,11 @@ __global__ void __launch_bounds__(256, 3) k_gather_tc(SceneDev sc, const float* 
                                                       Mlp3Dev presim, uint16_t* __restrict__ tok, float4* __restrict__ rgbm,
                                                       float4* __restrict__ dirs, float* __restrict__ sim8_out) {
   constexpr int SN = kNC;
-  __shared__ float s_sim[256][9];
-  __shared__ __align__(16) float s_w[8 * 32 + 32 + 32 * 32 + 32 + 32 * 16 + 16];
+  extern __shared__ __align__(16) uint8_t gsm[];
+  float* s_w = reinterpret_cast<float*>(gsm);
+  float(*s_sim)[9] = reinterpret_cast<float(*)[9]>(gsm + kGatherWFloats * 4);
+  float4* s_prj = reinterpret_cast<float4*>(gsm + kGatherWFloats * 4 + 256 * 9 * 4);
+  uint4* s_tap = reinterpret_cast<uint4*>(gsm + kGatherWFloats * 4 + 256 * 9 * 4 + 32 * NV * 16);
   constexpr int o_b0 = 8 * 32, o_w2 = o_b0 + 32, o_b2 = o_w2 + 32 * 32, o_w4 = o_b2 + 32, o_b4 = o_w4 + 32 * 16;
   {  // pre_sim_mlp weights -> shared memory
     for (int i = threadIdx.x; i < 8 * 32; i += 256) s_w[i] = __ldg(presim.w0 + i);
@@ -274,6 +311,8 @@ __global__ void __launch_bounds__(256, 3) k_gather_tc(SceneDev sc, const float* 
   const long long p0 = (long long)blockIdx.x * 256;
   const float fj = __ldg(freqs + j), pj = __ldg(phases + j);
   const size_t fstride = (size_t)sc.h * sc.w * kFeatC, istride = (size_t)sc.H * sc.W;
+  float4* my_prj = s_prj + sub * NV;
+  uint4* my_tap = s_tap + sub * (3 * NV) * 2;
   for (int round = 0; round < 8; ++round) {
     const long long p = p0 + round * 32 + sub;
     if (p >= P) break;
@@ -284,22 +323,44 @@ __global__ void __launch_bounds__(256, 3) k_gather_tc(SceneDev sc, const float* 
     const float y = __fadd_rn(sc.ray_o[1], __fmul_rn(zz, ri[1]));
     const float z = __fadd_rn(sc.ray_o[2], __fmul_rn(zz, ri[2]));
     const size_t sl = (size_t)tc_slot(p, half);
-    float u[NV], v[NV], qz[NV];
+    // ---- shared per-view work: projection + tap set-up, item k = flavour * NV + view
+    __syncwarp(gmask);                                   // the previous round's readers are done
 #pragma unroll
-    for (int n = 0; n < NV; ++n) project_pt(sc.P[n], x, y, z, u[n], v[n], qz[n]);
-    // ---- frustum volumes first (their 24 values go to every view row): blended over views with the summed weights
+    for (int k0 = 0; k0 < 3 * NV; k0 += 8) {
+      const int k = k0 + j;
+      if (k < 3 * NV) {
+        const int kind = k / NV, n = k - kind * NV;
+        float u, v, qz;
+        project_pt(sc.P[n], x, y, z, u, v, qz);
+        if (kind == 0) my_prj[n] = make_float4(u, v, qz, 0.f);
+        const bool big = (kind == 1);
+        const BilTaps t = bil_setup_rt(u, v, big ? sc.H : sc.h, big ? sc.W : sc.w, kind == 2, kind == 2);
+        my_tap[2 * k] = make_uint4((unsigned)t.i00, (unsigned)t.i01, (unsigned)t.i10, (unsigned)t.i11);
+        my_tap[2 * k + 1] = make_uint4(__float_as_uint(t.w00), __float_as_uint(t.w01), __float_as_uint(t.w10), __float_as_uint(t.w11));
+      }
+    }
+    __syncwarp(gmask);
+    auto taps_of = [&](int k) {
+      const uint4 a = my_tap[2 * k], b = my_tap[2 * k + 1];
+      BilTaps t;
+      t.i00 = (int)a.x; t.i01 = (int)a.y; t.i10 = (int)a.z; t.i11 = (int)a.w;
+      t.w00 = __uint_as_float(b.x); t.w01 = __uint_as_float(b.y); t.w10 = __uint_as_float(b.z); t.w11 = __uint_as_float(b.w);
+      return t;
+    };
+    // ---- frustum volumes (their 24 values go to every view row): blended over views with the summed weights
     float G[3] = {0.f, 0.f, 0.f}, Wsum = 0.f;
     {
       const float range = sc.far0 - sc.near0;
 #pragma unroll
       for (int n = 0; n < NV; ++n) {
-        const float zn = ((qz[n] - sc.near0) / range) * 2.f - 1.f;       // camera.py:399-400
+        const float4 pr = my_prj[n];
+        const float zn = ((pr.z - sc.near0) / range) * 2.f - 1.f;         // camera.py:399-400
         float f[3], wl = 0.f;
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
           const size_t vox = (size_t)sc.vd[s] * sc.vh[s] * sc.vw[s];
           float ws;
-          tri_fetch_lane(sc.vol_feat_cl[s] + n * vox * kVolC, sc.vol_w[s] + n * vox, sc.vd[s], sc.vh[s], sc.vw[s], u[n], v[n], zn,
+          tri_fetch_lane(sc.vol_feat_cl[s] + n * vox * kVolC, sc.vol_w[s] + n * vox, sc.vd[s], sc.vh[s], sc.vw[s], pr.x, pr.y, zn,
                          j, gmask, f[s], ws);
           wl += ws;                                                        // model.py:375-378
         }
@@ -319,10 +380,8 @@ __global__ void __launch_bounds__(256, 3) k_gather_tc(SceneDev sc, const float* 
 #pragma unroll
     for (int n = 0; n < NV; ++n) {
       uint16_t* row = tok + (sl * NV + n) * kDView;
-      const BilTaps tf = bil_setup<false, false>(u[n], v[n], sc.h, sc.w);
-      const float4 ft = bil_fetch32(sc.feat_cl + n * fstride, tf, j);
-      const BilTaps ti = bil_setup<false, false>(u[n], v[n], sc.H, sc.W);
-      const float4 c = bil_fetch_rgbd(sc.rgbd_cl + n * istride, ti);
+      const float4 ft = bil_fetch32(sc.feat_cl + n * fstride, taps_of(n), j);
+      const float4 c = bil_fetch_rgbd(sc.rgbd_cl + n * istride, taps_of(NV + n));
       const float zc = fmaf(sc.w2c_z[n][0], x, fmaf(sc.w2c_z[n][1], y, fmaf(sc.w2c_z[n][2], z, sc.w2c_z[n][3])));
       const float pe = __sinf(fmaf(c.w - zc, fj, pj));                     // ray_transformer.py:66,245 (|arg| < ~40)
       uint2 f;
@@ -334,8 +393,9 @@ __global__ void __launch_bounds__(256, 3) k_gather_tc(SceneDev sc, const float* 
       row[48 + j] = g2;
       row[72 + j] = (uint16_t)(umma::pack2<BF16>(pe, 0.f) & 0xffffu);
       if (j == 0) {
-        const bool inb = (u[n] <= 1.f) && (u[n] >= -1.f) && (v[n] <= 1.f) && (v[n] >= -1.f);
-        rgbm[sl * NV + n] = make_float4(c.x, c.y, c.z, (inb && qz[n] > 0.f) ? 1.f : 0.f);
+        const float4 pr = my_prj[n];
+        const bool inb = (pr.x <= 1.f) && (pr.x >= -1.f) && (pr.y <= 1.f) && (pr.y >= -1.f);
+        rgbm[sl * NV + n] = make_float4(c.x, c.y, c.z, (inb && pr.z > 0.f) ? 1.f : 0.f);
         const float sx = x - sc.cam_o[n][0], sy = y - sc.cam_o[n][1], sz = z - sc.cam_o[n][2];
         const float sn = 1.f / sqrtf(sx * sx + sy * sy + sz * sz);
         dirs[sl * NV + n] = make_float4(rx * rn - sx * sn, ry * rn - sy * sn, rz * rn - sz * sn, 0.f);
@@ -345,15 +405,16 @@ __global__ void __launch_bounds__(256, 3) k_gather_tc(SceneDev sc, const float* 
     {
       float acc = 0.f;
 #pragma unroll
-      for (int a = 0; a < NV - 1; ++a)
+      for (int a = 0; a < NV - 1; ++a) {
+        const BilTaps ta = taps_of(2 * NV + a);
 #pragma unroll
         for (int b = a + 1; b < NV; ++b) {
-          const BilTaps ta = bil_setup<true, true>(u[a], v[a], sc.h, sc.w);
-          const BilTaps tb = bil_setup<true, true>(u[b], v[b], sc.h, sc.w);
+          const BilTaps tb = taps_of(2 * NV + b);
           const float4 fa = bil_fetch32(sc.match_cl + (size_t)(a * (NV - 1) + (b - 1)) * fstride, ta, j);
           const float4 fb = bil_fetch32(sc.match_cl + (size_t)(b * (NV - 1) + a) * fstride, tb, j);
           acc += cos4(fa, fb);
         }
+      }
       const float sim = acc / (float)(NV * (NV - 1) / 2);
       s_sim[round * 32 + sub][j] = sim;
       if (sim8_out != nullptr) sim8_out[sl * 8 + j] = sim;
