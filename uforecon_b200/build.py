@@ -25,6 +25,8 @@ def _sources():
 def needs_build() -> bool:
     if not os.path.exists(OUT):
         return True
+    if "UFO_LIB_PATH" in os.environ:      # an explicitly selected (A/B) library is used as it is
+        return False
     t = os.path.getmtime(OUT)
     hdr = os.path.join(os.path.dirname(HERE), "include", "uforecon_b200.h")
     return any(os.path.getmtime(s) > t for s in _sources() + [hdr])

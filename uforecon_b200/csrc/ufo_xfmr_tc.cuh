@@ -210,23 +210,27 @@ __device__ __forceinline__ long long tc_slot(long long p, int half) { return (p 
 // Trilinear sample (align_corners=True, zeros) with one tap per lane: lane j of the 8-lane point group fetches the
 // whole 8-channel voxel of tap (dx,dy,dz) = (j&1, j>>1&1, j>>2), scales it by its tap weight, and a 3-step
 // reduce-scatter over the group leaves channel j of the interpolated feature in lane j (7 shuffles) and the
-// interpolated weight-volume value in every lane (3 shuffles).  Same taps and weights as tri_fetch, other summation order.
-__device__ __forceinline__ void tri_fetch_lane(const float* __restrict__ vf, const float* __restrict__ vw, int D, int H, int W,
-                                               float u, float v, float zn, int j, unsigned gmask, float& f_out, float& w_out) {
+// interpolated weight-volume value in every lane (3 shuffles).  Same taps and weights as tri_fetch, other summation
+// order.  Split in two halves so that the loads of several volumes can be in flight together.
+struct TriTap {
+  size_t idx;     // voxel index of this lane's tap (0 when the tap is out of range)
+  float wgt;      // trilinear weight of the tap (0 when out of range)
+};
+__device__ __forceinline__ TriTap tri_tap(int D, int H, int W, float u, float v, float zn, int j) {
   const float ix = gs_unnorm<true>(u, W), iy = gs_unnorm<true>(v, H), iz = gs_unnorm<true>(zn, D);
-  f_out = 0.f;
-  w_out = 0.f;
   const bool near_vol = (ix > -1.f) && (ix < (float)W) && (iy > -1.f) && (iy < (float)H) && (iz > -1.f) && (iz < (float)D);
-  if (!near_vol) return;                               // uniform over the 8-lane group
   const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
   const int dx = j & 1, dy = (j >> 1) & 1, dz = j >> 2;
   const int x = (int)fx + dx, y = (int)fy + dy, z = (int)fz + dz;
   const float wx = dx ? ix - fx : (fx + 1.f) - ix, wy = dy ? iy - fy : (fy + 1.f) - iy, wz = dz ? iz - fz : (fz + 1.f) - iz;
-  const bool ok = (x >= 0) && (x < W) && (y >= 0) && (y < H) && (z >= 0) && (z < D);
-  const float wgt = ok ? wx * wy * wz : 0.f;
-  const size_t idx = ok ? ((size_t)z * H + y) * W + x : 0;
-  float4 a = ldg4(vf + idx * kVolC), b = ldg4(vf + idx * kVolC + 4);
-  float ww = __ldg(vw + idx) * wgt;
+  const bool ok = near_vol && (x >= 0) && (x < W) && (y >= 0) && (y < H) && (z >= 0) && (z < D);
+  TriTap t;
+  t.wgt = ok ? wx * wy * wz : 0.f;
+  t.idx = ok ? ((size_t)z * H + y) * W + x : 0;
+  return t;
+}
+__device__ __forceinline__ void tri_reduce(float4 a, float4 b, float ww, float wgt, int j, unsigned gmask, float& f_out, float& w_out) {
+  ww *= wgt;
   a = f4_scale(a, wgt);
   b = f4_scale(b, wgt);
   const bool b2 = (j & 4) != 0, b1 = (j & 2) != 0, b0 = (j & 1) != 0;
@@ -284,8 +288,11 @@ constexpr int gather_tc_smem() { return kGatherWFloats * 4 + 256 * 9 * 4 + 32 * 
 // False / zeros on h x w; 1: colour+depth, same on H x W; 2: match maps, align_corners True / border on h x w) for
 // k = j, j+8, ..; results go through shared memory.  (The exact path k_gather recomputes them in every lane and,
 // for the match maps, for every pair: 3 NV + NV(NV-1) set-ups per lane instead of ceil(3 NV / 8).)
+#ifndef UFO_GATHER_MINB
+#define UFO_GATHER_MINB 3
+#endif
 template <int NV, bool BF16>
-__global__ void __launch_bounds__(256, 3) k_gather_tc(SceneDev sc, const float* __restrict__ rayinfo,
+__global__ void __launch_bounds__(256, UFO_GATHER_MINB) k_gather_tc(SceneDev sc, const float* __restrict__ rayinfo,
                                                       const float* __restrict__ zbuf, int R, int half,
                                                       const float* __restrict__ freqs, const float* __restrict__ phases,
                                                       Mlp3Dev presim, uint16_t* __restrict__ tok, float4* __restrict__ rgbm,
@@ -356,12 +363,23 @@ __global__ void __launch_bounds__(256, 3) k_gather_tc(SceneDev sc, const float* 
         const float4 pr = my_prj[n];
         const float zn = ((pr.z - sc.near0) / range) * 2.f - 1.f;         // camera.py:399-400
         float f[3], wl = 0.f;
+        TriTap tp[3];
+        float4 va[3], vb[3];
+        float vwt[3];
+#pragma unroll
+        for (int s = 0; s < 3; ++s) tp[s] = tri_tap(sc.vd[s], sc.vh[s], sc.vw[s], pr.x, pr.y, zn, j);
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {          // all 9 loads of this view in flight together
+          const size_t vox = (size_t)sc.vd[s] * sc.vh[s] * sc.vw[s];
+          const float* vf = sc.vol_feat_cl[s] + (n * vox + tp[s].idx) * kVolC;
+          va[s] = ldg4(vf);
+          vb[s] = ldg4(vf + 4);
+          vwt[s] = __ldg(sc.vol_w[s] + n * vox + tp[s].idx);
+        }
 #pragma unroll
         for (int s = 0; s < 3; ++s) {
-          const size_t vox = (size_t)sc.vd[s] * sc.vh[s] * sc.vw[s];
           float ws;
-          tri_fetch_lane(sc.vol_feat_cl[s] + n * vox * kVolC, sc.vol_w[s] + n * vox, sc.vd[s], sc.vh[s], sc.vw[s], pr.x, pr.y, zn,
-                         j, gmask, f[s], ws);
+          tri_reduce(va[s], vb[s], vwt[s], tp[s].wgt, j, gmask, f[s], ws);
           wl += ws;                                                        // model.py:375-378
         }
 #pragma unroll
