@@ -906,27 +906,34 @@ k_ray_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams prm
     if (prow >= P) return -1;
     return (SN == kNC) ? tc_slot(prow, 0) : tile * 128 + (perm ? (long long)perm[prow] : (long long)r);
   };
-  auto load_x = [&](long long tile) {
-    const long long ir = in_row_of(tile);
-    constexpr int NI = (10 + G - 1) / G;
+  // chunks g, g+4, g+8 (< 10) of the row: raw loads (issued early) and conversion + store (after the loads' latency)
+  float4 xr[6];
+  auto x_issue = [&](long long ir) {
 #pragma unroll
-    for (int i = 0; i < NI; ++i) {
-      const int c = g + G * i;
-      if (c < 10) {
-        float v[8];
-        if (ir >= 0) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(vout0 + (size_t)ir * kDView + 8 * c));
-          const float4 b = __ldg(reinterpret_cast<const float4*>(vout0 + (size_t)ir * kDView + 8 * c + 4));
-          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        } else {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) v[k] = 0.f;
-        }
-        st_chunk<BF16>(smem + R_X, r, c, v);
+    for (int i = 0; i < 3; ++i) {
+      const int c = g + 4 * i;
+      xr[2 * i] = xr[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < 10 && ir >= 0) {
+        xr[2 * i] = __ldg(reinterpret_cast<const float4*>(vout0 + (size_t)ir * kDView + 8 * c));
+        xr[2 * i + 1] = __ldg(reinterpret_cast<const float4*>(vout0 + (size_t)ir * kDView + 8 * c + 4));
       }
     }
   };
-  if ((long long)blockIdx.x < n_tiles) load_x(blockIdx.x);
+  auto x_store = [&]() {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int c = g + 4 * i;
+      if (c < 10) {
+        const float2 v[4] = {make_float2(xr[2 * i].x, xr[2 * i].y), make_float2(xr[2 * i].z, xr[2 * i].w),
+                             make_float2(xr[2 * i + 1].x, xr[2 * i + 1].y), make_float2(xr[2 * i + 1].z, xr[2 * i + 1].w)};
+        st_chunk2<BF16>(smem + R_X, r, c, v);
+      }
+    }
+  };
+  if ((long long)blockIdx.x < n_tiles) {
+    x_issue(in_row_of(blockIdx.x));
+    x_store();
+  }
   umma::fence_async_smem();
   umma::tc_fence_before();
   __syncthreads();
@@ -946,6 +953,8 @@ k_ray_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams prm
     const long long prow = tile * 128 + r;           // this thread's token: ray prow/SN, sorted sample prow%SN
     const bool row_ok = prow < P;
     const long long in_row = in_row_of(tile);
+    const bool has_next = tile + (long long)gridDim.x < n_tiles;
+    const long long in_row_nx = has_next ? in_row_of(tile + gridDim.x) : -1;     // its perm lookup completes under R1..R9
     // ---- R1: q|k|v = x . Wqkv^T   (K = 96: columns 88..95 hit zero weight columns); x was staged by the previous
     //      iteration (or the prologue) and fenced there
     if (tid == 0) {
@@ -965,22 +974,26 @@ k_ray_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams prm
       auto r2 = [&](auto GGc) {
         constexpr int GG = decltype(GGc)::value;
         constexpr int NI = (11 - GG + 3) / 4;
+        float2 a[NI][4], b[NI][4], d[NI][4];
 #pragma unroll
         for (int i = 0; i < NI; ++i) {
           const int c = GG + 4 * i;
-          float2 a[4], b[4], d[4];
-          tmem_ld8p(tlane + D_QKV + 8 * c, a);
-          tmem_ld8p(tlane + D_QKV + 88 + 8 * c, b);
-          tmem_ld8p(tlane + D_QKV + 176 + 8 * c, d);
-          umma::tmem_ld_wait();
+          tmem_ld8p(tlane + D_QKV + 8 * c, a[i]);
+          tmem_ld8p(tlane + D_QKV + 88 + 8 * c, b[i]);
+          tmem_ld8p(tlane + D_QKV + 176 + 8 * c, d[i]);
+        }
+        umma::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+          const int c = GG + 4 * i;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            a[k] = elu1_2(a[k]);
-            b[k] = elu1_2(b[k]);
+            a[i][k] = elu1_2(a[i][k]);
+            b[i][k] = elu1_2(b[i][k]);
           }
-          st_chunk2<BF16>(smem + R_Q, r, c, a);
-          st_chunk2<BF16>(smem + R_K, r, c, b);
-          st_chunk2<BF16>(smem + R_V, r, c, d);
+          st_chunk2<BF16>(smem + R_Q, r, c, a[i]);
+          st_chunk2<BF16>(smem + R_K, r, c, b[i]);
+          st_chunk2<BF16>(smem + R_V, r, c, d[i]);
         }
       };
       UFO_G_DISPATCH(r2)
@@ -1057,15 +1070,16 @@ k_ray_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams prm
       auto r6 = [&](auto GGc) {
         constexpr int GG = decltype(GGc)::value;
         constexpr int NI = (11 - GG + 3) / 4;
+        float v[NI][8];
+#pragma unroll
+        for (int i = 0; i < NI; ++i) umma::tmem_ld8(dm + 8 * (GG + 4 * i), v[i]);
+        umma::tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < NI; ++i) {
           const int c = GG + 4 * i;
-          float v[8];
-          umma::tmem_ld8(dm + 8 * c, v);
-          umma::tmem_ld_wait();
 #pragma unroll
-          for (int k = 0; k < 8; ++k) v[k] *= zr[(8 * c + k) / 11];      // static index: head of column 8c+k
-          st_chunk<BF16>(smem + R_M, r, c, v);
+          for (int k = 0; k < 8; ++k) v[i][k] *= zr[(8 * c + k) / 11];      // static index: head of column 8c+k
+          st_chunk<BF16>(smem + R_M, r, c, v[i]);
         }
       };
       UFO_G_DISPATCH(r6)
@@ -1118,27 +1132,26 @@ k_ray_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams prm
     umma::mbar_wait(bar, ph);
     ph ^= 1;
     umma::tc_fence_after();
-    const bool has_next = tile + (long long)gridDim.x < n_tiles;
     if (tid == 0 && has_next) bulk_load(smem + R_SLOTA, wimg + RW_QKV, 272 * 96 * 2, barA);
-    // x of the next tile: the concat operand is free from here on; its loads complete under the rest of this tile
-    if (has_next) load_x(tile + gridDim.x);
+    // x of the next tile: the concat operand is free from here on; the loads fly under the ReLU epilogue
+    if (has_next) x_issue(in_row_nx);
     // ---- R10: ReLU -> H1 operand (aliases K'/V' chunks 0..21)
     {
       auto r10 = [&](auto GGc) {
         constexpr int GG = decltype(GGc)::value;
         constexpr int NI = (22 - GG + 3) / 4;
+        float2 v[NI][4];
 #pragma unroll
-        for (int i = 0; i < NI; ++i) {
-          const int c = GG + 4 * i;
-          float2 v[4];
-          tmem_ld8p(tlane + D_ML0 + 8 * c, v);
-          umma::tmem_ld_wait();
-          *reinterpret_cast<uint4*>(tile_ptr(smem + R_K, r, c)) =
-              make_uint4(relu_pack2<BF16>(v[0]), relu_pack2<BF16>(v[1]), relu_pack2<BF16>(v[2]), relu_pack2<BF16>(v[3]));
-        }
+        for (int i = 0; i < NI; ++i) tmem_ld8p(tlane + D_ML0 + 8 * (GG + 4 * i), v[i]);
+        umma::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < NI; ++i)
+          *reinterpret_cast<uint4*>(tile_ptr(smem + R_K, r, GG + 4 * i)) =
+              make_uint4(relu_pack2<BF16>(v[i][0]), relu_pack2<BF16>(v[i][1]), relu_pack2<BF16>(v[i][2]), relu_pack2<BF16>(v[i][3]));
       };
       UFO_G_DISPATCH(r10)
     }
+    if (has_next) x_store();
     umma::fence_async_smem();
     umma::tc_fence_before();
     __syncthreads();
@@ -1159,39 +1172,35 @@ k_ray_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams prm
       auto ln2 = [&](auto GGc) {
         constexpr int GG = decltype(GGc)::value;
         constexpr int NI = (11 - GG + 3) / 4;
+        // fp32 residual input of this row (chunks < 10 from the view stage, chunk 10 = order encoding): issued first
+        float4 xa[3], xb[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const int c = GG + 4 * i;
+          xa[i] = xb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (c < 10) {
+            if (row_ok) {
+              xa[i] = __ldg(reinterpret_cast<const float4*>(vout0 + (size_t)in_row * kDView + 8 * c));
+              xb[i] = __ldg(reinterpret_cast<const float4*>(vout0 + (size_t)in_row * kDView + 8 * c + 4));
+            }
+          } else if (c == 10) {
+            xa[i] = __ldg(reinterpret_cast<const float4*>(pe_table + (r % SN) * 8));
+            xb[i] = __ldg(reinterpret_cast<const float4*>(pe_table + (r % SN) * 8 + 4));
+          }
+        }
         float2 v[NI][4];
         red[GG * 128 + r] = ln_load<GG, 11>(tlane + D_ML2, v);
         __syncthreads();
         const float2 st = ln_stats(red, r, 1.f / 88.f);
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-          constexpr int dummy = 0;
-          (void)dummy;
           const int c = GG + 4 * i;
           float hi[8], lo[8];
           if (c < 11) {
             float2 o2[4];
             ln_apply(v[i < NI ? i : 0], st, prm.n2w + 8 * (c < 11 ? c : 0), prm.n2b + 8 * (c < 11 ? c : 0), o2);
-            float x[8];
-            if (c < 10) {
-              if (row_ok) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(vout0 + (size_t)in_row * kDView + 8 * c));
-                const float4 b = __ldg(reinterpret_cast<const float4*>(vout0 + (size_t)in_row * kDView + 8 * c + 4));
-                x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
-              } else {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) x[k] = 0.f;
-              }
-            } else {
-#pragma unroll
-              for (int k = 0; k < 8; ++k) x[k] = __ldg(pe_table + (r % SN) * 8 + k);
-            }
-            float o[8];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              o[2 * k] = x[2 * k] + o2[k].x;
-              o[2 * k + 1] = x[2 * k + 1] + o2[k].y;
-            }
+            const float o[8] = {xa[i].x + o2[0].x, xa[i].y + o2[0].y, xa[i].z + o2[1].x, xa[i].w + o2[1].y,
+                                xb[i].x + o2[2].x, xb[i].y + o2[2].y, xb[i].z + o2[3].x, xb[i].w + o2[3].y};
 #pragma unroll
             for (int k = 0; k < 8; ++k) split_hi_lo<BF16>(o[k], hi[k], lo[k]);
             if (ray_out != nullptr && row_ok) {
