@@ -1,0 +1,68 @@
+"""GPU: the host-side mirror of the reference's method interface (uforecon_b200/renderer.py).
+
+``UFOReconRenderer.infer`` must be callable exactly like ``UFORecon.infer(extract_geometry=True)``
+(code1/model.py:393-478): same arguments, same return tuple, sampler uniforms drawn from torch's global CPU
+generator in the reference's order, so that ``torch.manual_seed`` reproduces the reference's sample positions.
+``render_depth_map`` is the chunk loop of ``extract_geometry`` (code1/model.py:814-826).
+"""
+import pytest
+import torch
+
+from conftest import make_case, rel_err
+from oracle import uforecon_oracle as orc
+from uforecon_b200 import synthetic
+from uforecon_b200._lib import UFO_MODE_FP32, UFO_MODE_TC
+from uforecon_b200.renderer import UFOReconRenderer, draw_uniforms
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def small():
+    batch, scene, sd = make_case(synthetic.UNFAVORABLE_VIEWS, (96, 64))
+    return batch, scene, sd
+
+
+def test_infer_signature_and_seeded_parity(small):
+    batch, scene, sd = small
+    ren = UFOReconRenderer(sd, mode=UFO_MODE_FP32)
+    ray_idx = torch.arange(1000, 1000 + 200)[None]                       # [1, RN] like torch.split(ray_idx_all, ...)
+    torch.manual_seed(11)
+    srdf, pts, depth, rgb = ren.infer(batch, ray_idx, scene["source_imgs_feat"], feature_volume=scene["feature_volume"],
+                                      extract_geometry=True, match_feature=scene["match_feature"])
+    assert tuple(srdf.shape) == (1, 200, 128) and tuple(pts.shape) == (1, 200, 128, 3)
+    assert tuple(depth.shape) == (1, 200) and tuple(rgb.shape) == (1, 200, 3)
+    torch.manual_seed(11)                                                 # the reference's draws: coarse, then fine
+    u_c, u_f = draw_uniforms(200)
+    with torch.no_grad():
+        o = orc.infer(batch, scene, sd, ray_idx[0], u_c, u_f)
+    assert rel_err(depth[0].cpu(), o["depth"]) <= 1e-4
+    assert rel_err(srdf[0].cpu(), o["srdf"]) <= 5e-4      # end to end through the importance sampler
+    assert rel_err(pts[0].cpu(), o["points"]) <= 1e-5
+    with pytest.raises(NotImplementedError):
+        ren.infer(batch, ray_idx, scene["source_imgs_feat"], feature_volume=scene["feature_volume"],
+                  extract_geometry=False, match_feature=scene["match_feature"])
+    ren.close()
+
+
+@pytest.mark.parametrize("mode", [UFO_MODE_FP32, UFO_MODE_TC])
+def test_render_depth_map_matches_chunked_infer(small, mode):
+    """One library call over the whole ray grid == the reference's loop over 800-ray chunks (same uniform draws)."""
+    batch, scene, sd = small
+    ren = UFOReconRenderer(sd, mode=mode, test_ray_num=800)
+    H, W = 64, 96
+    torch.manual_seed(5)
+    depth_mm, rgb = ren.render_depth_map(batch, scene["source_imgs_feat"], scene["feature_volume"], scene["match_feature"])
+    assert tuple(depth_mm.shape) == (H, W) and tuple(rgb.shape) == (H, W, 3)
+    torch.manual_seed(5)
+    cz = batch["cam_ray_d"][0][2].to(depth_mm.device)
+    scale = float(batch["scale_mat"][0][0, 0])
+    got_d, got_c = [], []
+    for ray_idx in torch.split(torch.arange(H * W), 800):                # extract_geometry's loop, model.py:814-823
+        _, _, d, c = ren.infer(batch, ray_idx[None], scene["source_imgs_feat"], feature_volume=scene["feature_volume"],
+                               extract_geometry=True, match_feature=scene["match_feature"])
+        got_d.append(d[0] * cz[ray_idx.to(cz.device)] * scale)
+        got_c.append(c[0])
+    ref_d, ref_c = torch.cat(got_d).view(H, W), torch.cat(got_c).view(H, W, 3)
+    assert torch.equal(depth_mm, ref_d) and torch.equal(rgb, ref_c)      # tiling never changes a bit
+    ren.close()
