@@ -367,6 +367,12 @@ def run_b200(args):
             costvol = bench_costvolume(args, dev)
         except Exception as ex:  # measurement extra: never fail the headline line
             costvol = {"error": str(ex)}
+    tsdf = None
+    if rank == 0 and world == 1 and not args.no_costvolume:
+        try:
+            tsdf = bench_tsdf(args, dev, None, None)
+        except Exception as ex:
+            tsdf = {"error": str(ex)}
 
     # ---- CPU baseline (rank 0, N=1 only)
     cpu = None
@@ -394,6 +400,7 @@ def run_b200(args):
             "roofline": roof,
             "rooflines": roofs,
             "costvolume": costvol,
+            "tsdf": tsdf,
             "profiled_ms_per_step": ms_prof_total / args.steps,
             "kernels": [{"name": n, "launches": c, "ms": round(ms, 3)} for n, c, ms in sorted(prof, key=lambda x: -x[2])[:12]],
             "cpu_baseline": cpu,
@@ -497,6 +504,42 @@ def bench_costvolume(args, dev):
         vw = vw_new
         del feats, sim
     return res
+
+
+def bench_tsdf(args, dev, depth_z, sc_batch):
+    """Next row N3: TSDF integration of depth maps (ufo_tsdf_integrate) - 16 synthetic views into a 512^3 volume."""
+    from uforecon_b200 import _lib
+    from uforecon_b200.tsdf import TSDFVolume
+    import numpy as np
+    H, W = 1216, 1600
+    n_views = 16
+    K = np.array([[2892.33, 0, 823.2], [0, 2883.18 * 1216 / 1200, 619.07 * 1216 / 1200], [0, 0, 1]], dtype=np.float32)
+    depths, poses = [], []
+    g = torch.Generator(device=dev).manual_seed(5)
+    for v in range(n_views):
+        th = 0.12 * v - 0.9
+        eye = 650.0 * np.array([np.sin(th), 0.05 * v, -np.cos(th)])
+        z = -eye / np.linalg.norm(eye)
+        x = np.cross(np.array([0, 1.0, 0]), z); x /= np.linalg.norm(x)
+        y = np.cross(z, x)
+        c2w = np.eye(4, dtype=np.float32); c2w[:3, 0], c2w[:3, 1], c2w[:3, 2], c2w[:3, 3] = x, y, z, eye
+        poses.append(c2w)
+        depths.append(600.0 + 60.0 * torch.rand(H, W, device=dev, generator=g))
+    vol = TSDFVolume(np.array([[-192.0, 192.0]] * 3), voxel_size=0.75, margin=3, device=dev)      # 512^3 voxels
+    vol.integrate_many(depths, [K] * n_views, poses)                                             # warm-up
+    _lib.profile_begin()
+    for _ in range(3):
+        vol.integrate_many(depths, [K] * n_views, poses)
+    prof = _lib.profile_end(16)
+    ms = sum(m for n, c, m in prof if n.startswith("k_tsdf")) / 3
+    vox = int(np.prod(vol._vol_dim))
+    upd = int((vol.device_volumes()[1] > 0).sum())
+    # algorithmic bytes of the fused launch: read + write (tsdf, weight) once per touched voxel, one 4-byte depth tap per
+    # voxel and view; the reference's kernel moves (tsdf, weight) once per VIEW
+    fused = upd * 16 + vox * n_views * 4
+    per_view = n_views * (upd * 16) + vox * n_views * 4
+    return {"voxels": vox, "views": n_views, "updated_voxels": upd, "kernel_ms": ms, "voxel_views_per_s": vox * n_views / (ms * 1e-3),
+            "fused_gbs": fused / (ms * 1e-3) / 1e9, "reference_schedule_bytes": per_view, "hbm_peak_gbs": peaks()["hbm_gbs"]}
 
 
 def main():

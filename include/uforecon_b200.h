@@ -213,6 +213,26 @@ int ufo_costvolume_stage(const float* const* feats, int32_t n_rot, int32_t n_vie
                          const float* depth_hyp, const float* view_w_in, const UfoPixelwiseNet* pw,
                          float* similarity, float* view_w_out, void* stream);
 
+/* TSDF integration of depth maps ("next" row N3; replaces the PyCUDA kernel `integrate`, tsdf_fusion.py:77-152, and
+ * the per-view loop of save_tsdf, tsdf_fusion.py:486-502).  tsdf / weight are [dev] fp32 volumes [X,Y,Z] (Z fastest,
+ * like the reference's numpy arrays), updated in place; views are integrated in array order with the reference's
+ * running average.  intr = cam_intr row-major 3x3, pose = camera-to-world 4x4 row-major (what the reference passes
+ * as cam_pose = inv(extrinsic)).  The reference's colour volume is never written by its kernel and has no entry here. */
+typedef struct {
+  int32_t dim[3];      /* voxels along x, y, z                                   */
+  float origin[3];     /* world position of voxel (0,0,0)  (TSDFVolume._vol_origin) */
+  float voxel_size;
+  float trunc_margin;  /* margin * voxel_size                                    */
+} UfoTsdfGrid;
+typedef struct {
+  const float* depth;  /* [dev] [im_h, im_w], 0 = invalid */
+  int32_t im_h, im_w;
+  float intr[9];
+  float pose[16];
+} UfoTsdfView;
+int ufo_tsdf_integrate(const UfoTsdfGrid* grid, float* tsdf, float* weight, const UfoTsdfView* views, int32_t n_views,
+                       float obs_weight, void* stream);
+
 /* Diagnostics: one-CTA tcgen05 GEMM through the library's own operand-staging and descriptor helpers
  * (csrc/ufo_umma.cuh).  mode 0: D[128,N] = A[128,K] . B[N,K]^T; mode 1: D = At[K,128]^T . Bt[K,N].
  * All [dev] fp32; operands are rounded to fp16 (bf16 != 0: bf16) on the way to shared memory. */

@@ -66,6 +66,14 @@ class UfoPixelwiseNet(C.Structure):
                                            "bn1_mean", "bn1_var", "conv2_w")] + [("conv2_b", C.c_float)]
 
 
+class UfoTsdfGrid(C.Structure):
+    _fields_ = [("dim", C.c_int32 * 3), ("origin", C.c_float * 3), ("voxel_size", C.c_float), ("trunc_margin", C.c_float)]
+
+
+class UfoTsdfView(C.Structure):
+    _fields_ = [("depth", C.c_void_p), ("im_h", C.c_int32), ("im_w", C.c_int32), ("intr", C.c_float * 9), ("pose", C.c_float * 16)]
+
+
 class UfoProfileEntry(C.Structure):
     _fields_ = [("name", C.c_char * 48), ("launches", C.c_int64), ("ms", C.c_double)]
 
@@ -75,6 +83,7 @@ EXPORTS = (
     "ufo_abi_version", "ufo_last_error", "ufo_device_info", "ufo_weights_create", "ufo_weights_destroy",
     "ufo_scene_create", "ufo_scene_destroy", "ufo_scene_device_bytes", "ufo_render_rays", "ufo_render_rays_host",
     "ufo_launch_count", "ufo_costvolume_stage", "ufo_debug_umma_selftest", "ufo_profile_begin", "ufo_profile_end",
+    "ufo_tsdf_integrate",
 )
 
 _lib = None
@@ -114,6 +123,8 @@ def load() -> C.CDLL:
                                          C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ufo_debug_umma_selftest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                             C.c_void_p]
+    lib.ufo_tsdf_integrate.argtypes = [C.POINTER(UfoTsdfGrid), C.c_void_p, C.c_void_p, C.POINTER(UfoTsdfView), C.c_int32, C.c_float,
+                                       C.c_void_p]
     lib.ufo_profile_end.argtypes = [C.POINTER(UfoProfileEntry), C.c_int32, C.POINTER(C.c_int32)]
     if lib.ufo_abi_version() != 1:
         raise UfoError(f"ABI version mismatch: library {lib.ufo_abi_version()} != binding 1")

@@ -1,4 +1,5 @@
 // C-ABI entry points of libuforecon_b200.so (declared in include/uforecon_b200.h).
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <map>
@@ -16,6 +17,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include "ufo_umma_selftest.cuh"
+#include "ufo_tsdf.cuh"
 
 namespace ufo {
 thread_local char g_err[512] = "";
@@ -845,6 +847,43 @@ extern "C" int ufo_costvolume_stage(const float* const* feats, int32_t N, int32_
   cudaFreeAsync(mats_dev, st);
   cudaFreeAsync((void*)src_ptrs_dev, st);
   return e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// TSDF integration (next row N3)
+// ------------------------------------------------------------------------------------------------
+extern "C" int ufo_tsdf_integrate(const UfoTsdfGrid* g, float* tsdf, float* weight, const UfoTsdfView* views, int32_t n_views,
+                                  float obs_weight, void* stream_) {
+  if (!g || !tsdf || !weight || (n_views > 0 && !views)) return fail(UFO_EINVAL, "ufo_tsdf_integrate: null argument");
+  if (g->dim[0] <= 0 || g->dim[1] <= 0 || g->dim[2] <= 0 || !(g->voxel_size > 0.f) || !(g->trunc_margin > 0.f))
+    return fail(UFO_EINVAL, "ufo_tsdf_integrate: bad grid");
+  if (n_views < 0) return fail(UFO_EINVAL, "ufo_tsdf_integrate: n_views < 0");
+  if (int e = check_device()) return e;
+  cudaStream_t st = (cudaStream_t)stream_;
+  int dev = 0, sms = 0;
+  UFO_CUDA(cudaGetDevice(&dev));
+  UFO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const long long total = (long long)g->dim[0] * g->dim[1] * g->dim[2];
+  const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sms * 16);
+  for (int v0 = 0; v0 < n_views; v0 += kTsdfMaxViews) {
+    TsdfLaunch L{};
+    L.n_views = std::min(kTsdfMaxViews, n_views - v0);
+    for (int i = 0; i < L.n_views; ++i) {
+      const UfoTsdfView& s = views[v0 + i];
+      if (!s.depth || s.im_h <= 0 || s.im_w <= 0) return fail(UFO_EINVAL, "ufo_tsdf_integrate: bad view %d", v0 + i);
+      TsdfViewDev& d = L.v[i];
+      d.depth = s.depth; d.im_h = s.im_h; d.im_w = s.im_w;
+      d.fx = s.intr[0]; d.cx = s.intr[2]; d.fy = s.intr[4]; d.cy = s.intr[5];
+      for (int a = 0; a < 3; ++a) {
+        for (int b = 0; b < 3; ++b) d.r[a * 3 + b] = s.pose[a * 4 + b];
+        d.t[a] = s.pose[a * 4 + 3];
+      }
+    }
+    UFO_KERNEL("k_tsdf_integrate", st, k_tsdf_integrate<<<grid, 256, 0, st>>>(tsdf, weight, g->dim[0], g->dim[1], g->dim[2], g->origin[0],
+                                                                            g->origin[1], g->origin[2], g->voxel_size, g->trunc_margin,
+                                                                            obs_weight, L));
+  }
+  return UFO_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
