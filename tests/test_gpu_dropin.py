@@ -66,3 +66,28 @@ def test_render_depth_map_matches_chunked_infer(small, mode):
     ref_d, ref_c = torch.cat(got_d).view(H, W), torch.cat(got_c).view(H, W, 3)
     assert torch.equal(depth_mm, ref_d) and torch.equal(rgb, ref_c)      # tiling never changes a bit
     ren.close()
+
+
+@pytest.mark.parametrize("mode", [UFO_MODE_FP32, UFO_MODE_TC])
+def test_host_buffer_entry_point_equals_device_call(small, mode, monkeypatch):
+    """ufo_render_rays_host (pinned host uniforms in, host depth/rgb out, uploads pipelined in column blocks) must
+    return exactly what ufo_render_rays returns for the same ray range."""
+    import ctypes as C
+    from uforecon_b200 import _lib
+    from uforecon_b200.renderer import HotPathWeights, Scene, render_rays
+    batch, scene, sd = small
+    monkeypatch.setenv("UFO_TC_CHUNK", "96")        # several upload blocks (4 chunks each) for this small ray count
+    monkeypatch.setenv("UFO_FP32_CHUNK", "96")
+    lib = _lib.load()
+    w = HotPathWeights(sd)
+    sc = Scene(batch, scene["source_imgs_feat"], scene["feature_volume"], scene["match_feature"])
+    n, begin = 1000, 321
+    u_c, u_f = synthetic.sampler_uniforms(n, seed=9)
+    ref = render_rays(sc, w, None, n, u_c, u_f, mode, ray_begin=begin, want=("depth_z", "rgb"))
+    u_ch, u_fh = u_c.contiguous().pin_memory(), u_f.contiguous().pin_memory()
+    dz, rgb = torch.empty(n).pin_memory(), torch.empty(n, 3).pin_memory()
+    _lib.check(lib.ufo_render_rays_host(sc.handle, w.handle, begin, n, u_ch.data_ptr(), u_fh.data_ptr(), mode, dz.data_ptr(),
+                                        rgb.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    assert torch.equal(dz, ref["depth_z"].cpu()) and torch.equal(rgb, ref["rgb"].cpu())
+    sc.close()
+    w.close()

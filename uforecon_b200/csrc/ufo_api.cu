@@ -54,6 +54,9 @@ using namespace ufo;
 // ------------------------------------------------------------------------------------------------
 // handles
 // ------------------------------------------------------------------------------------------------
+static int fp32_chunk_rays();
+static int tc_chunk_rays(int sms);
+
 static int check_device() {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
@@ -373,6 +376,11 @@ extern "C" void ufo_scene_destroy(UfoScene* s) {
   cudaFree(s->tws.base);
   cudaFree(s->u_dev);
   cudaFree(s->out_dev);
+  if (s->copy_st) {
+    cudaEventDestroy(s->copy_ev[0]);
+    cudaEventDestroy(s->copy_ev[1]);
+    cudaStreamDestroy(s->copy_st);
+  }
   delete s;
 }
 
@@ -706,16 +714,38 @@ extern "C" int ufo_render_rays_host(const UfoScene* sc, const UfoWeights* w, int
       UFO_CUDA(cudaMalloc(&sc->out_dev, sizeof(float) * 5 * (size_t)n_rays));
       sc->u_cap = (size_t)n_rays;
     }
+    if (!sc->copy_st) {
+      UFO_CUDA(cudaStreamCreateWithFlags(&sc->copy_st, cudaStreamNonBlocking));
+      UFO_CUDA(cudaEventCreateWithFlags(&sc->copy_ev[0], cudaEventDisableTiming));
+      UFO_CUDA(cudaEventCreateWithFlags(&sc->copy_ev[1], cudaEventDisableTiming));
+    }
   }
   float* u_c = sc->u_dev;
   float* u_f = sc->u_dev + (size_t)kNC * n_rays;
-  UFO_CUDA(cudaMemcpyAsync(u_c, u_c_host, sizeof(float) * kNC * (size_t)n_rays, cudaMemcpyHostToDevice, st));
-  UFO_CUDA(cudaMemcpyAsync(u_f, u_f_host, sizeof(float) * kNC * (size_t)n_rays, cudaMemcpyHostToDevice, st));
   UfoRenderOut o{};
   o.depth_z = sc->out_dev;
   o.rgb = sc->out_dev + n_rays;
   o.depth = sc->out_dev + 4 * (size_t)n_rays;
-  if (int e = ufo_render_rays(sc, w, nullptr, ray_begin, n_rays, u_c, u_f, n_rays, mode, &o, nullptr, stream_)) return e;
+  // The sampler uniforms ([64][n_rays] per sampler, 512 B per ray) are the bulk of the transfer: they go up in column
+  // blocks on a private copy stream, and the render of block k overlaps the upload of block k+1.
+  int sms = 0, dev = 0;
+  UFO_CUDA(cudaGetDevice(&dev));
+  UFO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int64_t block = (int64_t)(mode == UFO_MODE_FP32 ? fp32_chunk_rays() : tc_chunk_rays(sms)) * 4;
+  const size_t pitch = sizeof(float) * (size_t)n_rays;
+  int k = 0;
+  for (int64_t off = 0; off < n_rays; off += block, ++k) {
+    const int nb = (int)std::min<int64_t>(block, n_rays - off);
+    UFO_CUDA(cudaMemcpy2DAsync(u_c + off, pitch, u_c_host + off, pitch, sizeof(float) * nb, kNC, cudaMemcpyHostToDevice, sc->copy_st));
+    UFO_CUDA(cudaMemcpy2DAsync(u_f + off, pitch, u_f_host + off, pitch, sizeof(float) * nb, kNC, cudaMemcpyHostToDevice, sc->copy_st));
+    UFO_CUDA(cudaEventRecord(sc->copy_ev[k & 1], sc->copy_st));
+    UFO_CUDA(cudaStreamWaitEvent(st, sc->copy_ev[k & 1], 0));
+    UfoRenderOut ob = o;
+    ob.depth_z = o.depth_z + off;
+    ob.rgb = o.rgb + 3 * off;
+    ob.depth = o.depth + off;
+    if (int e = ufo_render_rays(sc, w, nullptr, ray_begin + off, nb, u_c + off, u_f + off, n_rays, mode, &ob, nullptr, stream_)) return e;
+  }
   UFO_CUDA(cudaMemcpyAsync(depth_z_host, o.depth_z, sizeof(float) * n_rays, cudaMemcpyDeviceToHost, st));
   UFO_CUDA(cudaMemcpyAsync(rgb_host, o.rgb, sizeof(float) * 3 * (size_t)n_rays, cudaMemcpyDeviceToHost, st));
   UFO_CUDA(cudaStreamSynchronize(st));

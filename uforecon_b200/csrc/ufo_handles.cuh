@@ -58,6 +58,8 @@ struct UfoScene {
   mutable float* u_dev = nullptr;      // staging for ufo_render_rays_host
   mutable float* out_dev = nullptr;
   mutable size_t u_cap = 0;
+  mutable cudaStream_t copy_st = nullptr;   // uploads of ufo_render_rays_host, overlapped with the render
+  mutable cudaEvent_t copy_ev[2] = {nullptr, nullptr};
   mutable std::mutex mu;
 };
 
