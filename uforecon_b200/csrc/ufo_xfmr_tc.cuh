@@ -502,7 +502,7 @@ k_view_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams p
   constexpr int L = NV + 1, PPT = 128 / L, ROWS = PPT * L;
   constexpr int NPF = (1280 + kThreads - 1) / kThreads;   // 16-byte token pieces per thread per tile
   constexpr uint32_t FMT = BF16 ? umma::kFmtBF16 : umma::kFmtF16;
-  constexpr uint32_t D_QKV = 0, D_RAD = 240, D_ML0 = 256, D_MRG = 416, D_ML2 = 0;   // TMEM columns
+  constexpr uint32_t D_QKV = 0, D_RAD0 = 240, D_RAD1 = 496, D_ML0 = 256, D_MRG = 416, D_ML2 = 0;   // TMEM columns
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   uint8_t* const smem = tc_smem;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + V_BAR);
@@ -567,8 +567,74 @@ k_view_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams p
   };
   prefetch(blockIdx.x);
 
+  // P11: radiance-head tail 16 -> 8 -> 1 (hidden units g and g+4 per thread), masked softmax over views, colour blend.
+  // Reads the accumulator D_RAD[parity] of a finished tile; called while the next tile's QKV GEMM is in flight.
+  auto rad_tail = [&](int pb, uint32_t drad) {
+  {
+    float h[16];
+    umma::tmem_ld16(tlane + drad, h);
+    umma::tmem_ld_wait();
+    auto tail = [&](auto GGc) {
+      constexpr int GG = decltype(GGc)::value;
+#pragma unroll
+      for (int o = 0; o < 16; ++o) h[o] = fmaxf(h[o], 0.f);      // bias and direction terms came through the GEMM
+      float part = 0.f;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int o = GG + 4 * j;
+        float a0 = prm.rb2[o], a1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          a0 = fmaf(h[i], prm.rw2[o][i], a0);
+          a1 = fmaf(h[i + 1], prm.rw2[o][i + 1], a1);
+        }
+        part = fmaf(fmaxf(a0 + a1, 0.f), prm.rw4[o], part);
+      }
+      omg[GG * 128 + r] = part;
+    };
+    UFO_G_DISPATCH(tail)
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (tid < PPT && pb + tid < P) {
+    const size_t p = (size_t)slot_of(pb + tid);
+    float om[NV];
+    float4 col[NV];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int n = 0; n < NV; ++n) {
+      col[n] = __ldg(rgbm + p * NV + n);
+      const int rr = tid * L + 1 + n;
+      const float w = prm.rb4 + ((omg[rr] + omg[128 + rr]) + (omg[256 + rr] + omg[384 + rr]));
+      om[n] = (col[n].w == 0.f) ? -1e9f : w;                     // ray_transformer.py:316
+      mx = fmaxf(mx, om[n]);
+    }
+    float den = 0.f;
+#pragma unroll
+    for (int n = 0; n < NV; ++n) {
+      om[n] = ex2_ftz((om[n] - mx) * 1.4426950408889634f);
+      den += om[n];
+    }
+    float cr = 0.f, cg = 0.f, cb = 0.f;
+#pragma unroll
+    for (int n = 0; n < NV; ++n) {
+      const float pw = om[n] / den;
+      cr = fmaf(col[n].x, pw, cr);
+      cg = fmaf(col[n].y, pw, cg);
+      cb = fmaf(col[n].z, pw, cb);
+    }
+    radiance[p] = make_float4(cr, cg, cb, 0.f);
+  }
+  };
+  bool have_prev = false;
+  int prev_pbase = 0;
+  uint32_t prev_drad = D_RAD0, par = 0;
+
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int pbase = tile * PPT;
+    const uint32_t D_RAD = par ? D_RAD1 : D_RAD0;
     // ---- P0: token rows of this tile (prefetched) -> X (A operand, K = 80)
 #pragma unroll
     for (int k = 0; k < NPF; ++k)
@@ -591,6 +657,7 @@ k_view_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams p
     prefetch(tile + gridDim.x);
     float4 my_dir = make_float4(0.f, 0.f, 0.f, 0.f);
     if (view_row) my_dir = __ldg(dirs + my_slot * NV + (l - 1));
+    if (have_prev) rad_tail(prev_pbase, prev_drad);          // the previous tile's head tail, under this tile's QKV GEMM
     umma::mbar_wait(bar, ph);
     ph ^= 1;
     umma::tc_fence_after();
@@ -786,67 +853,15 @@ k_view_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams p
     umma::mbar_wait(bar, ph);
     ph ^= 1;
     umma::tc_fence_after();
-    // ---- P11: head tail 16 -> 8 -> 1 (hidden units g and g+4 per thread), masked softmax, colour blend
-    {
-      float h[16];
-      umma::tmem_ld16(tlane + D_RAD, h);
-      umma::tmem_ld_wait();
-      auto tail = [&](auto GGc) {
-        constexpr int GG = decltype(GGc)::value;
-#pragma unroll
-        for (int o = 0; o < 16; ++o) h[o] = fmaxf(h[o], 0.f);      // bias and direction terms came through the GEMM
-        float part = 0.f;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          constexpr int dummy = 0;
-          (void)dummy;
-          const int o = GG + 4 * j;
-          float a0 = prm.rb2[o], a1 = 0.f;
-#pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            a0 = fmaf(h[i], prm.rw2[o][i], a0);
-            a1 = fmaf(h[i + 1], prm.rw2[o][i + 1], a1);
-          }
-          part = fmaf(fmaxf(a0 + a1, 0.f), prm.rw4[o], part);
-        }
-        omg[GG * 128 + r] = part;
-      };
-      UFO_G_DISPATCH(tail)
-    }
-    umma::tc_fence_before();
-    __syncthreads();
-    if (tid < PPT && pbase + tid < P) {
-      const size_t p = (size_t)slot_of(pbase + tid);
-      float om[NV];
-      float4 col[NV];
-      float mx = -INFINITY;
-#pragma unroll
-      for (int n = 0; n < NV; ++n) {
-        col[n] = __ldg(rgbm + p * NV + n);
-        const int rr = tid * L + 1 + n;
-        const float w = prm.rb4 + ((omg[rr] + omg[128 + rr]) + (omg[256 + rr] + omg[384 + rr]));
-        om[n] = (col[n].w == 0.f) ? -1e9f : w;                     // ray_transformer.py:316
-        mx = fmaxf(mx, om[n]);
-      }
-      float den = 0.f;
-#pragma unroll
-      for (int n = 0; n < NV; ++n) {
-        om[n] = ex2_ftz((om[n] - mx) * 1.4426950408889634f);
-        den += om[n];
-      }
-      float cr = 0.f, cg = 0.f, cb = 0.f;
-#pragma unroll
-      for (int n = 0; n < NV; ++n) {
-        const float pw = om[n] / den;
-        cr = fmaf(col[n].x, pw, cr);
-        cg = fmaf(col[n].y, pw, cg);
-        cb = fmaf(col[n].z, pw, cb);
-      }
-      radiance[p] = make_float4(cr, cg, cb, 0.f);
-    }
+    // P11 (head tail, softmax, colour blend) of this tile is deferred: it runs under the QKV GEMM of the next tile
+    have_prev = true;
+    prev_pbase = pbase;
+    prev_drad = D_RAD;
+    par ^= 1;
     // the next tile's P0 writes X only after this tile's last MMA (P10) has completed: guaranteed by the wait above;
     // omg is next written after several more block-wide barriers
   }
+  if (have_prev) rad_tail(prev_pbase, prev_drad);
   umma::tc_fence_before();
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc(tmem, 512);
