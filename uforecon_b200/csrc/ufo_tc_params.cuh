@@ -32,7 +32,8 @@ constexpr uint32_t V_KV = V_E + 2 * kChunk;         // K',V' staging [8 heads][1
 constexpr uint32_t V_RED = V_KV + 20 * kChunk;      // float2 [kGroups][128]  LayerNorm partials
 constexpr uint32_t V_OMG = V_RED + 8 * kGroups * 128;  // float [kGroups][128]   radiance-head partials
 constexpr uint32_t V_BAR = V_OMG + 4 * kGroups * 128;
-constexpr uint32_t V_SMEM = V_BAR + 64;
+constexpr uint32_t V_RGBM = V_BAR + 64;             // float4 [2][128]: (r,g,b,mask) of the tile's (point, view) pairs, double-buffered
+constexpr uint32_t V_SMEM = V_RGBM + 2 * 128 * 16;
 static_assert(V_SMEM <= 232448, "view-stage shared memory exceeds the 227 KB opt-in limit");
 }  // namespace tc
 

@@ -509,6 +509,7 @@ k_view_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams p
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + V_BAR + 16);
   float2* red = reinterpret_cast<float2*>(smem + V_RED);
   float* omg = reinterpret_cast<float*>(smem + V_OMG);
+  float4* s_rgbm = reinterpret_cast<float4*>(smem + V_RGBM);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, g = warp >> 2, r = q * 32 + lane;
   const int pl = r / L, l = r - pl * L;
@@ -569,7 +570,7 @@ k_view_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams p
 
   // P11: radiance-head tail 16 -> 8 -> 1 (hidden units g and g+4 per thread), masked softmax over views, colour blend.
   // Reads the accumulator D_RAD[parity] of a finished tile; called while the next tile's QKV GEMM is in flight.
-  auto rad_tail = [&](int pb, uint32_t drad) {
+  auto rad_tail = [&](int pb, uint32_t drad, uint32_t cpar) {
   {
     float h[16];
     umma::tmem_ld16(tlane + drad, h);
@@ -605,7 +606,7 @@ k_view_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams p
     float mx = -INFINITY;
 #pragma unroll
     for (int n = 0; n < NV; ++n) {
-      col[n] = __ldg(rgbm + p * NV + n);
+      col[n] = s_rgbm[cpar * 128 + tid * NV + n];          // staged by the tile itself (P5), no global latency here
       const int rr = tid * L + 1 + n;
       const float w = prm.rb4 + ((omg[rr] + omg[128 + rr]) + (omg[256 + rr] + omg[384 + rr]));
       om[n] = (col[n].w == 0.f) ? -1e9f : w;                     // ray_transformer.py:316
@@ -655,9 +656,23 @@ k_view_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams p
       issue_gemm_sub(tmem + D_RAD, sm_base + V_X, sm_base + V_WRAD, 16, 0, 10, umma::make_idesc(128, 16, FMT, false, false), 0);
     }
     prefetch(tile + gridDim.x);
+    // relative direction of this row's (point, view): loaded as float2 + float - a float4 load would leave the unused .w
+    // register pending, and the next writer of that register would wait for the whole load (WAW on the scoreboard)
     float4 my_dir = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (view_row) my_dir = __ldg(dirs + my_slot * NV + (l - 1));
-    if (have_prev) rad_tail(prev_pbase, prev_drad);          // the previous tile's head tail, under this tile's QKV GEMM
+    if (view_row) {
+      const float* dp = reinterpret_cast<const float*>(dirs + my_slot * NV + (l - 1));
+      const float2 dxy = __ldg(reinterpret_cast<const float2*>(dp));
+      my_dir.x = dxy.x;
+      my_dir.y = dxy.y;
+      my_dir.z = __ldg(dp + 2);
+    }
+    // colour + mask of this tile's (point, view) pairs: loaded now, parked in shared memory at P5, used by rad_tail
+    float4 my_col = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid < PPT * NV) {
+      const int pp = pbase + tid / NV;
+      if (pp < P) my_col = __ldg(rgbm + (size_t)slot_of(pp) * NV + (tid % NV));
+    }
+    if (have_prev) rad_tail(prev_pbase, prev_drad, par ^ 1);   // the previous tile's head tail, under this tile's QKV GEMM
     umma::mbar_wait(bar, ph);
     ph ^= 1;
     umma::tc_fence_after();
@@ -756,6 +771,7 @@ k_view_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams p
     ph ^= 1;
     umma::tc_fence_after();
     // ---- P5: LayerNorm 1 -> second half of the concat operand     (transformer.py:56)
+    if (tid < PPT * NV) s_rgbm[par * 128 + tid] = my_col;
     {
       auto ln1 = [&](auto GGc) {
         constexpr int GG = decltype(GGc)::value;
@@ -861,7 +877,7 @@ k_view_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams p
     // the next tile's P0 writes X only after this tile's last MMA (P10) has completed: guaranteed by the wait above;
     // omg is next written after several more block-wide barriers
   }
-  if (have_prev) rad_tail(prev_pbase, prev_drad);
+  if (have_prev) rad_tail(prev_pbase, prev_drad, par ^ 1);
   umma::tc_fence_before();
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc(tmem, 512);
