@@ -91,3 +91,21 @@ def test_host_buffer_entry_point_equals_device_call(small, mode, monkeypatch):
     assert torch.equal(dz, ref["depth_z"].cpu()) and torch.equal(rgb, ref["rgb"].cpu())
     sc.close()
     w.close()
+
+
+def test_render_depth_map_device_rng(small):
+    """device-side uniforms: same distribution of jitter, so the depth map agrees with the CPU-seeded one up to the
+    sampling noise of the quadrature (a loose statistical bound), and two seeds differ."""
+    batch, scene, sd = small
+    ren = UFOReconRenderer(sd, mode=UFO_MODE_TC)
+    torch.manual_seed(1)
+    d_ref, _ = ren.render_depth_map(batch, scene["source_imgs_feat"], scene["feature_volume"], scene["match_feature"])
+    torch.cuda.manual_seed(1)
+    d_a, c_a = ren.render_depth_map(batch, scene["source_imgs_feat"], scene["feature_volume"], scene["match_feature"], device_rng=True)
+    torch.cuda.manual_seed(2)
+    d_b, _ = ren.render_depth_map(batch, scene["source_imgs_feat"], scene["feature_volume"], scene["match_feature"], device_rng=True)
+    assert torch.isfinite(d_a).all() and torch.isfinite(c_a).all()
+    assert not torch.equal(d_a, d_b)
+    rel = float(((d_a - d_ref).abs() / d_ref.abs().clamp_min(1e-6)).median())
+    assert rel < 2e-2, rel
+    ren.close()

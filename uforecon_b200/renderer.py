@@ -252,24 +252,31 @@ class UFOReconRenderer:
         r = render_rays(scene, self.weights, ray_idx[0], RN, u_c, u_f, self.mode, want=("depth", "rgb", "srdf", "points"))
         return r["srdf"][None], r["points"][None], r["depth"][None], r["rgb"][None]
 
-    def render_depth_map(self, batch, source_imgs_feat, feature_volume, match_feature, chunk: Optional[int] = None):
+    def render_depth_map(self, batch, source_imgs_feat, feature_volume, match_feature, chunk: Optional[int] = None,
+                         device_rng: bool = False):
         """The chunk loop of ``extract_geometry`` (model.py:814-826): depth [H,W] in mm, rgb [H,W,3].
 
-        With ``chunk=None`` the whole ray grid goes through one library call per ``test_ray_num`` draw group
-        only logically: uniforms are still drawn per reference chunk (800 rays) so that results do not
-        depend on how the library tiles the work.
+        The whole ray grid goes through one library call.  By default the sampler uniforms are still drawn per
+        reference chunk (``test_ray_num`` rays, coarse then fine) from torch's CPU generator, so the result is the one
+        the reference's loop produces for the same seed and does not depend on how the library tiles the work.
+        ``device_rng=True`` draws them on the GPU instead (torch's CUDA generator): statistically the same jitter, not
+        the reference's bit stream - the 250 M CPU draws per 1600x1216 map otherwise cost about as much as the render.
         """
         scene = self._scene_for(batch, source_imgs_feat, feature_volume, match_feature)
         H, W = scene.H, scene.W
         n = H * W
-        step = self.test_ray_num
-        u_c = torch.empty(UFO_N_COARSE, n, pin_memory=True)
-        u_f = torch.empty(UFO_N_FINE, n, pin_memory=True)
-        for s in range(0, n, step):                     # reference draw order: per 800-ray chunk, coarse then fine
-            e = min(n, s + step)
-            a, b = draw_uniforms(e - s)
-            u_c[:, s:e] = a
-            u_f[:, s:e] = b
+        if device_rng:
+            u_c = torch.rand(UFO_N_COARSE, n, device=self.device)
+            u_f = torch.rand(UFO_N_FINE, n, device=self.device)
+        else:
+            step = self.test_ray_num
+            u_c = torch.empty(UFO_N_COARSE, n, pin_memory=True)
+            u_f = torch.empty(UFO_N_FINE, n, pin_memory=True)
+            for s in range(0, n, step):                 # reference draw order: per 800-ray chunk, coarse then fine
+                e = min(n, s + step)
+                a, b = draw_uniforms(e - s)
+                u_c[:, s:e] = a
+                u_f[:, s:e] = b
         r = render_rays(scene, self.weights, None, n, u_c, u_f, self.mode, ray_begin=0, want=("depth_z", "rgb"))
         depth_mm = (r["depth_z"] * scene.scale).view(H, W)
         return depth_mm, r["rgb"].view(H, W, 3)
