@@ -978,7 +978,44 @@ k_ray_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams prm
     bulk_load(smem + R_SLOTB, wimg + RW_MRG, 96 * 96 * 2, barB);
   }
   // TMEM columns
-  constexpr uint32_t D_QKV = 0, D_KV = 272, D_MSG = 0, D_MRG = 96, D_ML0 = 192, D_ML2 = 0, D_DEN = 96;
+  constexpr uint32_t D_QKV = 0, D_KV = 272, D_MSG = 0, D_MRG = 96, D_ML0 = 192, D_ML2 = 0, D_DEN = 464;
+
+  // R14: DensityMLP tail 32 -> 16 -> 1 in fp32 (hidden units g, g+4, g+8, g+12 per thread) of a finished tile, read from
+  // its accumulator D_DEN; called while the next tile's QKV GEMM is in flight (D_DEN has its own TMEM columns).
+  auto srdf_tail = [&](long long pr, bool ok) {
+  {
+    float h[32];
+    umma::tmem_ld16(tlane + D_DEN, h);
+    umma::tmem_ld16(tlane + D_DEN + 16, h + 16);
+    umma::tmem_ld_wait();
+    float* part_s = reinterpret_cast<float*>(smem + R_SCR);     // the split operands are dead (MMA completed)
+    auto tail = [&](auto GGc) {
+      constexpr int GG = decltype(GGc)::value;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) h[i] = fmaxf(h[i] + prm.db0[i], 0.f);
+      float part = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int o = GG + 4 * j;
+        float2 acc = make_float2(prm.db2[o], 0.f);
+#pragma unroll
+        for (int i = 0; i < 32; i += 2)
+          acc = __ffma2_rn(make_float2(h[i], h[i + 1]), make_float2(prm.dw2[o][i], prm.dw2[o][i + 1]), acc);
+        part = fmaf(fmaxf(acc.x + acc.y, 0.f), prm.dw4[o], part);
+      }
+      part_s[GG * 128 + r] = part;
+    };
+    UFO_G_DISPATCH(tail)
+    umma::tc_fence_before();
+    __syncthreads();
+    if (g == 0 && ok) srdf[pr] = prm.db4 + ((part_s[r] + part_s[128 + r]) + (part_s[256 + r] + part_s[384 + r]));
+  }
+    __syncthreads();   // the partial-sum scratch lives in V' chunks that the next R2 rewrites
+  };
+  bool have_prev = false, prev_ok = false;
+  long long prev_prow = 0;
 
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long prow = tile * 128 + r;           // this thread's token: ray prow/SN, sorted sample prow%SN
@@ -996,6 +1033,7 @@ k_ray_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams prm
       issue_gemm_sub(tmem + D_QKV + 176, sm_base + R_X, sm_base + R_SLOTA, 272, 176, 12, umma::make_idesc(128, 96, FMT, false, false), 0);
       umma::commit(bar);
     }
+    if (have_prev) srdf_tail(prev_prow, prev_ok);       // the previous tile's SRDF tail, under this tile's QKV GEMM
     umma::mbar_wait(bar, ph);
     ph ^= 1;
     umma::tc_fence_after();
@@ -1266,38 +1304,13 @@ k_ray_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams prm
     umma::mbar_wait(bar, ph);
     ph ^= 1;
     umma::tc_fence_after();
-    // ---- R14: DensityMLP tail 32 -> 16 -> 1 in fp32, hidden units g, g+4, g+8, g+12 per thread
-    {
-      float h[32];
-      umma::tmem_ld16(tlane + D_DEN, h);
-      umma::tmem_ld16(tlane + D_DEN + 16, h + 16);
-      umma::tmem_ld_wait();
-      float* part_s = reinterpret_cast<float*>(smem + R_SCR);     // the split operands are dead (MMA completed)
-      auto tail = [&](auto GGc) {
-        constexpr int GG = decltype(GGc)::value;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) h[i] = fmaxf(h[i] + prm.db0[i], 0.f);
-        float part = 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          constexpr int dummy = 0;
-          (void)dummy;
-          const int o = GG + 4 * j;
-          float2 acc = make_float2(prm.db2[o], 0.f);
-#pragma unroll
-          for (int i = 0; i < 32; i += 2)
-            acc = __ffma2_rn(make_float2(h[i], h[i + 1]), make_float2(prm.dw2[o][i], prm.dw2[o][i + 1]), acc);
-          part = fmaf(fmaxf(acc.x + acc.y, 0.f), prm.dw4[o], part);
-        }
-        part_s[GG * 128 + r] = part;
-      };
-      UFO_G_DISPATCH(tail)
-      umma::tc_fence_before();
-      __syncthreads();
-      if (g == 0 && row_ok) srdf[prow] = prm.db4 + ((part_s[r] + part_s[128 + r]) + (part_s[256 + r] + part_s[384 + r]));
-    }
+    // R14 (SRDF tail) of this tile is deferred: it runs under the QKV GEMM of the next tile
+    have_prev = true;
+    prev_prow = prow;
+    prev_ok = row_ok;
     __syncthreads();   // scratch / Q' / V' regions are rewritten by the next tile's R2
   }
+  if (have_prev) srdf_tail(prev_prow, prev_ok);
   umma::tc_fence_before();
   __syncthreads();
   if (warp == 0) umma::tmem_dealloc(tmem, 512);
