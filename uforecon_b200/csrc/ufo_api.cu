@@ -424,11 +424,7 @@ static int ws_ensure(const UfoScene* sc, int rays) {
 template <int K, int N, bool R>
 static int launch_linear(const float* X, int ldx, const float* W, float* Y, int ldy, long long M, int sms, cudaStream_t st) {
   const size_t smem = sizeof(float) * ((size_t)K * N + 64 * K);
-  static bool attr_set = false;
-  if (!attr_set) {
-    UFO_CUDA(cudaFuncSetAttribute(k_linear<K, N, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  UFO_SMEM_ATTR((k_linear<K, N, R>), (int)smem);
   const long long tiles = (M + 63) / 64;
   const int grid = (int)(tiles < sms ? tiles : sms);
   static char name[40] = "";

@@ -66,6 +66,20 @@ inline int fail(int code, const char* fmt, ...) {
       return ::ufo::fail(UFO_ECUDA, "%s:%d kernel launch: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
   } while (0)
 
+// Opt-in dynamic shared memory size of a kernel, set once per (call site, device): function attributes are per device,
+// and one process may drive several.
+#define UFO_SMEM_ATTR(kernel, bytes)                                                                     \
+  do {                                                                                                   \
+    static std::atomic<unsigned long long> _done{0};                                                     \
+    int _dev = 0;                                                                                        \
+    UFO_CUDA(cudaGetDevice(&_dev));                                                                      \
+    const unsigned long long _bit = 1ull << (_dev & 63);                                                 \
+    if (!(_done.load(std::memory_order_relaxed) & _bit)) {                                               \
+      UFO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+      _done.fetch_or(_bit, std::memory_order_relaxed);                                                   \
+    }                                                                                                    \
+  } while (0)
+
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // Per-kernel device-time accounting (ufo_profile_begin / ufo_profile_end): when enabled, a

@@ -15,20 +15,12 @@ static int launch_tc_pass(const UfoScene* sc, const UfoWeights* w, int R, int ha
   const long long P = (long long)R * kNC;
   const int f = BF16 ? 0 : 1;
   {
-    static bool attr = false;
-    if (!attr) {
-      UFO_CUDA(cudaFuncSetAttribute(k_gather_tc<NV, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gather_tc_smem<NV>()));
-      attr = true;
-    }
+    UFO_SMEM_ATTR((k_gather_tc<NV, BF16>), gather_tc_smem<NV>());
   }
   UFO_KERNEL("k_gather_tc", st, k_gather_tc<NV, BF16><<<cdiv(P, 256), 256, gather_tc_smem<NV>(), st>>>(sc->d, ws.rayinfo, z, R, half, w->freqs, w->phases, w->pre_sim,
                                                                                   ws.tok, ws.rgbm, ws.dirs, want_sim8 ? ws.sim8 : nullptr));
   {
-    static bool attr = false;
-    if (!attr) {
-      UFO_CUDA(cudaFuncSetAttribute(k_view_tc<NV, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::V_SMEM));
-      attr = true;
-    }
+    UFO_SMEM_ATTR((k_view_tc<NV, BF16>), (int)tc::V_SMEM);
     constexpr int PPT = 128 / (NV + 1);
     const long long tiles = (P + PPT - 1) / PPT;
     const int grid = (int)(tiles < sms ? tiles : sms);
@@ -38,14 +30,12 @@ static int launch_tc_pass(const UfoScene* sc, const UfoWeights* w, int R, int ha
   if (half == 0) {
     const long long tiles = (P + 127) / 128;
     const int grid = (int)(tiles < sms ? tiles : sms);
-    static bool attr = false;
-    if (!attr) { UFO_CUDA(cudaFuncSetAttribute(k_ray_tc<kNC, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::R_SMEM)); attr = true; }
+    UFO_SMEM_ATTR((k_ray_tc<kNC, BF16>), (int)tc::R_SMEM);
     UFO_KERNEL("k_ray_tc", st, k_ray_tc<kNC, BF16><<<grid, tc::kThreads, tc::R_SMEM, st>>>(w->tc.ray_img[f], w->tc.rp, ws.vout0, w->pe_table, nullptr, P, ws.srdf, ray_out_tap));
   } else {
     const long long tiles = R;
     const int grid = (int)(tiles < sms ? tiles : sms);
-    static bool attr = false;
-    if (!attr) { UFO_CUDA(cudaFuncSetAttribute(k_ray_tc<kNS, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::R_SMEM)); attr = true; }
+    UFO_SMEM_ATTR((k_ray_tc<kNS, BF16>), (int)tc::R_SMEM);
     UFO_KERNEL("k_ray_tc", st, k_ray_tc<kNS, BF16><<<grid, tc::kThreads, tc::R_SMEM, st>>>(w->tc.ray_img[f], w->tc.rp, ws.vout0, w->pe_table, ws.perm, (long long)R * kNS, ws.srdf, ray_out_tap));
   }
   return UFO_OK;
