@@ -213,6 +213,14 @@ int ufo_costvolume_stage(const float* const* feats, int32_t n_rot, int32_t n_vie
                          const float* depth_hyp, const float* view_w_in, const UfoPixelwiseNet* pw,
                          float* similarity, float* view_w_out, void* stream);
 
+/* Alternative feature grid of --volume_type featuregrid (row a19): FeatureVolume.forward up to its 3-D regulariser
+ * (code1/feature_volume.py:40-92).  feats [dev] [NV,32,h,w]; source_poses [host] [NV,4,4] world->NDC; linear = the
+ * module's nn.Sequential (32->32 ReLU, 32->16 ReLU, 16->8; torch [out,in] layout, host); out [dev] [16,reso,reso,reso]
+ * in the (C, Z, Y, X) order the reference hands to VolumeRegularization: channels 0..7 masked mean over views,
+ * 8..15 masked variance. */
+int ufo_feature_grid(const float* feats, int32_t n_views, int32_t h, int32_t w, const float* source_poses, int32_t reso,
+                     const UfoMlp3* linear, float* out, void* stream);
+
 /* TSDF integration of depth maps ("next" row N3; replaces the PyCUDA kernel `integrate`, tsdf_fusion.py:77-152, and
  * the per-view loop of save_tsdf, tsdf_fusion.py:486-502).  tsdf / weight are [dev] fp32 volumes [X,Y,Z] (Z fastest,
  * like the reference's numpy arrays), updated in place; views are integrated in array order with the reference's

@@ -360,3 +360,32 @@ def cost_volume_stage(features: List[torch.Tensor], proj_matrices: torch.Tensor,
         w_sum = w_sum + vw.unsqueeze(1)
     out_vw = torch.cat(vws, 1) if view_weights is None else view_weights
     return sim_sum / w_sum, out_vw
+
+
+# ----------------------------------------------------------------------------------------------
+# a19 (alt)  FeatureVolume.forward up to the 3-D regulariser      code1/feature_volume.py:40-92
+# ----------------------------------------------------------------------------------------------
+def feature_grid_meanvar(feats: torch.Tensor, source_poses: torch.Tensor, lin: Dict[str, torch.Tensor], reso: int) -> torch.Tensor:
+    """feats [NV,32,h,w]; source_poses [NV,4,4] world->NDC; lin = {'0.weight','0.bias','2.weight',...,'4.bias'} of
+    ``FeatureVolume.linear`` (32->32->16->8).  Returns the tensor handed to ``volume_regularization``:
+    [16, Z, Y, X] = (masked mean | masked variance over views) of the compressed features on the reso^3 grid."""
+    NV = feats.shape[0]
+    line = np.linspace(0, reso - 1, reso) * 2 / (reso - 1) - 1                       # feature_volume.py:23-25 (float64)
+    x, y, z = np.meshgrid(line, line, line, indexing="ij")
+    xyz = torch.tensor(np.stack([x, y, z])).type_as(source_poses).reshape(3, -1)     # :48-49
+    homo = torch.cat([xyz, torch.ones_like(xyz[0:1])], 0)                            # [4, XYZ]
+    q = (source_poses @ homo[None].expand(NV, 4, -1))[:, :3]                         # :55-56
+    mask_z = (q[:, 2] > 0).float()                                                   # :57-58
+    uv = (q / q[:, 2:3])[:, :2].permute(0, 2, 1)                                     # [NV, XYZ, 2]   :61-63
+    inb = ((uv[..., 0] <= 1.) & (uv[..., 0] >= -1.) & (uv[..., 1] <= 1.) & (uv[..., 1] >= -1.)).float()
+    f = F.grid_sample(feats, uv[:, :, None, :], mode="bilinear", padding_mode="zeros", align_corners=False)[..., 0]  # [NV,32,XYZ]
+    mask = inb * mask_z                                                              # :74
+    weight = (mask / (mask.sum(0, keepdim=True) + 1e-8))[..., None]                  # [NV, XYZ, 1]  :79-80
+    c = f.permute(0, 2, 1)                                                           # [NV, XYZ, 32]
+    c = F.relu(F.linear(c, lin["0.weight"], lin["0.bias"]))
+    c = F.relu(F.linear(c, lin["2.weight"], lin["2.bias"]))
+    c = F.linear(c, lin["4.weight"], lin["4.bias"])                                  # [NV, XYZ, 8]  :83
+    mean = (c * weight).sum(0, keepdim=True)                                         # :86
+    var = (weight * (c - mean) ** 2).sum(0)                                          # :87
+    mv = torch.cat([mean[0], var], -1).view(reso, reso, reso, 16)                    # [X,Y,Z,C]     :91
+    return mv.permute(3, 2, 1, 0).contiguous()                                       # [C,Z,Y,X]     :92

@@ -69,3 +69,31 @@ def similarity_volume(features: Sequence[torch.Tensor], proj_matrices: torch.Ten
                                             _stream_ptr(dev)))
         torch.cuda.current_stream(dev).synchronize()
     return sim, vw_out
+
+
+def feature_grid(feats: torch.Tensor, batch: Dict[str, torch.Tensor], linear: Dict[str, torch.Tensor], volume_reso: int,
+                 device=None) -> torch.Tensor:
+    """``FeatureVolume.forward(feats, batch)`` up to its 3-D regulariser (code1/feature_volume.py:40-92), the alternative
+    ``--volume_type featuregrid``.  feats [1,NV,32,h,w]; ``linear`` = state dict of ``FeatureVolume.linear``
+    (keys '0.weight' ... '4.bias').  Returns ``volume_mean_var`` [1,16,Z,Y,X], the input of ``volume_regularization``."""
+    lib = _lib.load()
+    dev = torch.device(device if device is not None else "cuda")
+    B, NV, Cc, h, w = feats.shape
+    if B != 1 or Cc != 32:
+        raise ValueError("feats must be [1, NV, 32, h, w]")
+    keep = []
+
+    def hp(name):
+        t = _host_f32(linear[name]).reshape(-1).contiguous()
+        keep.append(t)
+        return t.data_ptr()
+
+    m = _lib.UfoMlp3()
+    m.w0, m.b0, m.w2, m.b2, m.w4, m.b4 = hp("0.weight"), hp("0.bias"), hp("2.weight"), hp("2.bias"), hp("4.weight"), hp("4.bias")
+    f = _dev_f32(feats[0], dev)
+    poses = _host_f32(batch["source_poses"][0])
+    out = torch.empty(1, 16, volume_reso, volume_reso, volume_reso, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.ufo_feature_grid(f.data_ptr(), NV, h, w, poses.data_ptr(), volume_reso, C.byref(m), out.data_ptr(), _stream_ptr(dev)))
+        torch.cuda.current_stream(dev).synchronize()
+    return out

@@ -18,6 +18,7 @@
 #include <cuda_fp16.h>
 #include "ufo_umma_selftest.cuh"
 #include "ufo_tsdf.cuh"
+#include "ufo_fgrid.cuh"
 
 namespace ufo {
 thread_local char g_err[512] = "";
@@ -872,6 +873,50 @@ extern "C" int ufo_costvolume_stage(const float* const* feats, int32_t N, int32_
   cudaFreeAsync(cl, st);
   cudaFreeAsync(mats_dev, st);
   cudaFreeAsync((void*)src_ptrs_dev, st);
+  return e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// alternative feature grid (row a19)
+// ------------------------------------------------------------------------------------------------
+extern "C" int ufo_feature_grid(const float* feats, int32_t nv, int32_t h, int32_t w, const float* poses, int32_t reso,
+                                const UfoMlp3* lin, float* out, void* stream_) {
+  if (!feats || !poses || !lin || !out) return fail(UFO_EINVAL, "ufo_feature_grid: null argument");
+  if (!lin->w0 || !lin->b0 || !lin->w2 || !lin->b2 || !lin->w4 || !lin->b4) return fail(UFO_EINVAL, "ufo_feature_grid: missing MLP tensor");
+  if (nv < 1 || nv > UFO_MAX_VIEWS || h <= 0 || w <= 0 || reso < 2) return fail(UFO_EINVAL, "ufo_feature_grid: bad size");
+  if (int e = check_device()) return e;
+  cudaStream_t st = (cudaStream_t)stream_;
+  FGridViews V{};
+  V.nv = nv;
+  for (int v = 0; v < nv; ++v) memcpy(V.P[v], poses + 16 * v, sizeof(float) * 12);
+  std::vector<float> wts;
+  wts.insert(wts.end(), lin->w0, lin->w0 + 32 * 32);
+  wts.insert(wts.end(), lin->b0, lin->b0 + 32);
+  wts.insert(wts.end(), lin->w2, lin->w2 + 16 * 32);
+  wts.insert(wts.end(), lin->b2, lin->b2 + 16);
+  wts.insert(wts.end(), lin->w4, lin->w4 + 8 * 16);
+  wts.insert(wts.end(), lin->b4, lin->b4 + 8);
+  float *cl = nullptr, *wd = nullptr;
+  const size_t fl = (size_t)nv * kFeatC * h * w;
+  UFO_CUDA(cudaMallocAsync((void**)&cl, sizeof(float) * fl, st));
+  UFO_CUDA(cudaMallocAsync((void**)&wd, sizeof(float) * wts.size(), st));
+  int e = repack_cl<kFeatC>(feats, cl, (long long)h * w, nv, st);
+  if (!e) {
+    cudaError_t ce = cudaMemcpyAsync(wd, wts.data(), sizeof(float) * wts.size(), cudaMemcpyHostToDevice, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);     // host vector goes out of scope below
+    if (ce != cudaSuccess) e = fail(UFO_ECUDA, "ufo_feature_grid: %s", cudaGetErrorString(ce));
+  }
+  if (!e) {
+    const long long total = (long long)reso * reso * reso;
+    [&]() -> int {
+      UFO_KERNEL("k_feature_grid", st, k_feature_grid<<<cdiv(total, 128), 128, 0, st>>>(cl, h, w, reso, V, wd, out));
+      return UFO_OK;
+    }();
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) e = fail(UFO_ECUDA, "ufo_feature_grid: %s", cudaGetErrorString(ce));
+  }
+  cudaFreeAsync(cl, st);
+  cudaFreeAsync(wd, st);
   return e;
 }
 
