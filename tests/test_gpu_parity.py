@@ -211,3 +211,29 @@ def test_api_errors():
     assert r["depth"].numel() == 0
     sc.close()
     w.close()
+
+
+def test_asymmetric_match_maps_use_both_slots():
+    """The reference samples view a's slot (b-1) at uv_a and view b's slot a at uv_b (model.py:273-285).  Its encoder
+    stores the same map in both slots, which the library detects and exploits; when a caller passes
+    different data in the two slots the result must still follow the reference."""
+    from uforecon_b200.renderer import HotPathWeights, Scene, render_rays
+    batch, scene, sd = make_case(synthetic.UNFAVORABLE_VIEWS, (96, 64))
+    scene = dict(scene)
+    m = scene["match_feature"][0].clone()
+    m[0, 2, :32] += 0.25 * torch.randn(m[0, 2, :32].shape, generator=torch.Generator().manual_seed(3))   # view 2, slot 0 = pair (0,2)
+    scene["match_feature"] = [m]
+    n = 96
+    ray_idx = torch.arange(0, 96 * 64, 64)[:n]
+    u_c, u_f = synthetic.sampler_uniforms(n, seed=8)
+    w = HotPathWeights(sd)
+    sc = Scene(batch, scene["source_imgs_feat"], scene["feature_volume"], scene["match_feature"])
+    r = render_rays(sc, w, ray_idx, n, u_c, u_f, UFO_MODE_FP32, want=("depth", "z"), taps=("sim8",))
+    r = {k: v.cpu() for k, v in r.items()}
+    d = batch["ray_d"][0][:, ray_idx].t()
+    pts = (batch["ray_o"][0][None, None] + r["z"][:, :, None] * d[:, None, :]).float()
+    with torch.no_grad():
+        o = orc.sample2rgb(batch, scene, sd, pts, r["z"], detail=True)
+    assert rel_err(r["sim8"], o["sim8"]) <= 2e-5
+    sc.close()
+    w.close()

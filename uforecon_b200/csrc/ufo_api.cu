@@ -337,6 +337,19 @@ extern "C" int ufo_scene_create(const UfoSceneDesc* d, UfoScene** out, void* str
   if ((e = repack_cl<kFeatC>(d->match_feats, match_cl, hw, nv * (nv - 1), st))) { ufo_scene_destroy(sc); return e; }
   UFO_KERNEL("k_pack_rgbd", st, k_pack_rgbd<<<cdiv(HW * nv, 256), 256, 0, st>>>(d->source_imgs, d->depth_info, rgbd, HW, nv));
   D.feat_cl = feat_cl; D.rgbd_cl = rgbd; D.match_cl = match_cl;
+  {  // the reference stores every pair map twice; when the two copies are bit-identical both samples of a
+     // pair read the same copy, which halves the working set of the dominant gather at large NV
+    int* flag = nullptr;
+    UFO_CUDA(cudaMalloc(&flag, sizeof(int)));
+    UFO_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+    UFO_KERNEL("k_match_sym_check", st, k_match_sym_check<<<dim3(64, nv, nv), 256, 0, st>>>(d->match_feats, nv, hw, flag));
+    int differ = 1;
+    cudaError_t ce = cudaMemcpyAsync(&differ, flag, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    cudaFree(flag);
+    if (ce != cudaSuccess) { ufo_scene_destroy(sc); return fail(UFO_ECUDA, "ufo_scene_create: %s", cudaGetErrorString(ce)); }
+    D.match_sym = differ ? 0 : 1;
+  }
   for (int s = 0; s < 3; ++s) {
     D.vd[s] = d->vol_d[s]; D.vh[s] = d->vol_h[s]; D.vw[s] = d->vol_w[s];
     const long long vox = (long long)D.vd[s] * D.vh[s] * D.vw[s];

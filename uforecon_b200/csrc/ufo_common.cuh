@@ -28,6 +28,8 @@ struct SceneDev {
   const float* feat_cl;         // [NV][h][w][32]
   const float4* rgbd_cl;        // [NV][H][W] (r,g,b,mvs_depth)
   const float* match_cl;        // [NV][NV-1][h][w][32]
+  int match_sym;                // 1: slot (b, a) holds the same map as slot (a, b-1) for every pair a < b (SURVEY.md F8,
+                                //    verified bit for bit at scene creation): both samples of a pair then read slot (a, b-1)
   const float* vol_feat_cl[3];  // [NV][D][hs][ws][8]
   const float* vol_w[3];        // [NV][D][hs][ws]
   const float* ray_d;           // [3][H*W]

@@ -40,4 +40,19 @@ static __global__ void __launch_bounds__(256) k_pack_rgbd(const float* __restric
   out[i] = make_float4(__ldg(im + s), __ldg(im + S + s), __ldg(im + 2 * S + s), __ldg(depth + n * S + s));
 }
 
+// Are the two copies of every pair map identical?  match [NV][(NV-1)*32][S] (reference layout): slot (a, b-1) vs slot
+// (b, a) for a < b, compared bit for bit; *differ is set to 1 on the first mismatch.
+static __global__ void __launch_bounds__(256) k_match_sym_check(const float* __restrict__ match, int NV, long long S, int* __restrict__ differ) {
+  const long long per = 32 * S;                       // floats of one pair map
+  const int a = blockIdx.y, b = blockIdx.z;
+  if (a >= b) return;
+  const unsigned* pa = reinterpret_cast<const unsigned*>(match) + ((long long)a * (NV - 1) + (b - 1)) * per;
+  const unsigned* pb = reinterpret_cast<const unsigned*>(match) + ((long long)b * (NV - 1) + a) * per;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (long long)gridDim.x * blockDim.x)
+    if (__ldg(pa + i) != __ldg(pb + i)) {
+      *differ = 1;
+      return;
+    }
+}
+
 }  // namespace ufo

@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(256, UFO_GATHER_MINB) k_gather_tc(SceneDev sc,
         for (int b = a + 1; b < NV; ++b) {
           const BilTaps tb = taps_of(2 * NV + b);
           const float4 fa = bil_fetch32(sc.match_cl + (size_t)(a * (NV - 1) + (b - 1)) * fstride, ta, j);
-          const float4 fb = bil_fetch32(sc.match_cl + (size_t)(b * (NV - 1) + a) * fstride, tb, j);
+          const float4 fb = bil_fetch32(sc.match_cl + (size_t)(sc.match_sym ? a * (NV - 1) + (b - 1) : b * (NV - 1) + a) * fstride, tb, j);
           acc += cos4(fa, fb);
         }
       }
