@@ -445,39 +445,43 @@ __global__ void __launch_bounds__(256, UFO_GATHER_MINB) k_gather_tc(SceneDev sc,
   float s[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = s_sim[threadIdx.x][i];
-  float h1[32];
+  // layers as packed fp32x2 FMAs over input pairs: acc.x collects even inputs, acc.y odd inputs
+  const float2 s01 = make_float2(s[0], s[1]), s23 = make_float2(s[2], s[3]), s45 = make_float2(s[4], s[5]), s67 = make_float2(s[6], s[7]);
+  float2 h1[16];
 #pragma unroll
   for (int o = 0; o < 32; ++o) {
     const float4 wa = *reinterpret_cast<const float4*>(s_w + o * 8), wb = *reinterpret_cast<const float4*>(s_w + o * 8 + 4);
-    float a0 = fmaf(s[0], wa.x, s_w[o_b0 + o]), a1 = s[1] * wa.y;
-    a0 = fmaf(s[2], wa.z, a0); a1 = fmaf(s[3], wa.w, a1);
-    a0 = fmaf(s[4], wb.x, a0); a1 = fmaf(s[5], wb.y, a1);
-    a0 = fmaf(s[6], wb.z, a0); a1 = fmaf(s[7], wb.w, a1);
-    h1[o] = fmaxf(a0 + a1, 0.f);
+    float2 acc = __fmul2_rn(s01, make_float2(wa.x, wa.y));
+    acc = __ffma2_rn(s23, make_float2(wa.z, wa.w), acc);
+    acc = __ffma2_rn(s45, make_float2(wb.x, wb.y), acc);
+    acc = __ffma2_rn(s67, make_float2(wb.z, wb.w), acc);
+    const float v = fmaxf((acc.x + acc.y) + s_w[o_b0 + o], 0.f);
+    if (o & 1) h1[o >> 1].y = v; else h1[o >> 1].x = v;
   }
-  float h2[32];
+  float2 h2[16];
 #pragma unroll
   for (int o = 0; o < 32; ++o) {
-    float a0 = s_w[o_b2 + o], a1 = 0.f;
+    float2 acc = make_float2(s_w[o_b2 + o], 0.f);
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       const float4 w = *reinterpret_cast<const float4*>(s_w + o_w2 + o * 32 + i);
-      a0 = fmaf(h1[i], w.x, a0); a1 = fmaf(h1[i + 1], w.y, a1);
-      a0 = fmaf(h1[i + 2], w.z, a0); a1 = fmaf(h1[i + 3], w.w, a1);
+      acc = __ffma2_rn(h1[i >> 1], make_float2(w.x, w.y), acc);
+      acc = __ffma2_rn(h1[(i >> 1) + 1], make_float2(w.z, w.w), acc);
     }
-    h2[o] = fmaxf(a0 + a1, 0.f);
+    const float v = fmaxf(acc.x + acc.y, 0.f);
+    if (o & 1) h2[o >> 1].y = v; else h2[o >> 1].x = v;
   }
   float o16[16];
 #pragma unroll
   for (int o = 0; o < 16; ++o) {
-    float a0 = s_w[o_b4 + o], a1 = 0.f;
+    float2 acc = make_float2(s_w[o_b4 + o], 0.f);
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       const float4 w = *reinterpret_cast<const float4*>(s_w + o_w4 + o * 32 + i);
-      a0 = fmaf(h2[i], w.x, a0); a1 = fmaf(h2[i + 1], w.y, a1);
-      a0 = fmaf(h2[i + 2], w.z, a0); a1 = fmaf(h2[i + 3], w.w, a1);
+      acc = __ffma2_rn(h2[i >> 1], make_float2(w.x, w.y), acc);
+      acc = __ffma2_rn(h2[(i >> 1) + 1], make_float2(w.z, w.w), acc);
     }
-    o16[o] = a0 + a1;
+    o16[o] = acc.x + acc.y;
   }
   const uint4 lo = tc::pack8<BF16>(o16), hi = tc::pack8<BF16>(o16 + 8);
   const size_t sl = (size_t)tc_slot(p, half);
