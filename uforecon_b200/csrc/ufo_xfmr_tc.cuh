@@ -586,8 +586,6 @@ k_view_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams p
       float part = 0.f;
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        constexpr int dummy = 0;
-        (void)dummy;
         const int o = GG + 4 * j;
         float a0 = prm.rb2[o], a1 = 0.f;
 #pragma unroll
@@ -786,8 +784,6 @@ k_view_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams p
         const float2 st = ln_stats(red, r, 1.f / 80.f);
 #pragma unroll
         for (int i = 0; i < NI; ++i) {
-          constexpr int dummy = 0;
-          (void)dummy;
           const int c = GG + 4 * i;
           float2 o[4];
           ln_apply(v[i], st, prm.n1w + 8 * c, prm.n1b + 8 * c, o);
@@ -933,8 +929,6 @@ k_ray_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams prm
     float one[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};                    // ones columns: D rows 88..95 = sum_s K'_s
     st_chunk<BF16>(smem + R_V, r, 11, one);
   }
-  const uint32_t tmem_dummy = 0;
-  (void)tmem_dummy;
   // x of a tile: token-0 output of the view stage at slot(ray, evaluation index) -> 16-bit A operand chunks 0..9
   auto in_row_of = [&](long long tile) -> long long {
     const long long prow = tile * 128 + r;
@@ -1000,8 +994,6 @@ k_ray_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams prm
       float part = 0.f;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        constexpr int dummy = 0;
-        (void)dummy;
         const int o = GG + 4 * j;
         float2 acc = make_float2(prm.db2[o], 0.f);
 #pragma unroll
@@ -1103,8 +1095,6 @@ k_ray_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams prm
           uint8_t* kvbd = smem + (sq == 0 ? R_K : R_V);        // [96 rows b][96 cols a], chunk stride 96*16
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
-            constexpr int dummy = 0;
-            (void)dummy;
             const int c = GG + 4 * i;
             float v[8];
             umma::tmem_ld8(tlane + D_KV + 96 * sq + 8 * c, v);
