@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py - rays/s and seconds per DTU-shaped depth map of the per-ray rendering hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--mode tc|fp32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--mode tc16|tc|fp32]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
@@ -27,6 +27,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -341,6 +342,15 @@ def run_b200(args):
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     e2e_value = world * n_rays * k_e2e / (ms_e2e * 1e-3)
 
+    # ---- accuracy of this mode at THIS workload (outside every timed region): a band of rows rendered in the measured
+    #      mode and in fp32 mode (the 1e-5 parity path) with the same uniforms -> the north-star tolerance figures
+    accuracy = None
+    if rank == 0 and args.mode != "fp32":
+        try:
+            accuracy = measure_accuracy(lib, sc, weights, batch, mode, u_c, u_f, n_rays, W, H, stream)
+        except Exception as ex:  # reported extra: never fail the headline line
+            accuracy = {"error": str(ex)}
+
     # ---- strong-scaling extra: ONE depth map with rows sharded over the ranks (+ gather to rank 0)
     sharded_s = None
     begin, n_mine = ufodist.shard_rows(H, W, world, rank)
@@ -396,6 +406,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": 16 * n_rays, "steps": k_e2e,
                     "api": "ufo_render_rays_host (pinned host uniforms in, pinned host depth/rgb out)"},
             "gpu_launches": int(launches),
+            "accuracy": accuracy,
             "clocks": clk,
             "roofline": roof,
             "rooflines": roofs,
@@ -412,6 +423,39 @@ def run_b200(args):
     weights.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_accuracy(lib, sc, weights, batch, mode, u_c, u_f, n_rays, W, H, stream, rows=16):
+    """Tensor-core mode vs fp32 mode on `rows` image rows from the middle of the map: p99 depth error as a fraction of the
+    depth interval and colour PSNR (BASELINE.json north star: <= 0.005 and >= 50 dB).  Rays whose in-image test is decided
+    by the last bits of the projection are left out of the PSNR (see tests/test_gpu_tc.py)."""
+    import ctypes as C
+    from uforecon_b200 import _lib
+    k = min(n_rays, rows * W)
+    begin = ((n_rays - k) // 2 // W) * W
+    dev = u_c.device
+    res = {}
+    for name, m in (("tc", mode), ("ref", _lib.UFO_MODE_FP32)):
+        d, r, z = torch.empty(k, device=dev), torch.empty(k, 3, device=dev), torch.empty(k, 128, device=dev)
+        o = _lib.UfoRenderOut()
+        o.depth, o.rgb, o.z = d.data_ptr(), r.data_ptr(), z.data_ptr()
+        _lib.check(lib.ufo_render_rays(sc.handle, weights.handle, None, begin, k, u_c.data_ptr() + 4 * begin,
+                                       u_f.data_ptr() + 4 * begin, n_rays, m, C.byref(o), None, stream.cuda_stream))
+        res[name] = (d, r, z)
+    torch.cuda.synchronize()
+    near, far = float(batch["near_fars"][0, 0, 0]), float(batch["near_fars"][0, 0, 1])
+    de = (res["tc"][0] - res["ref"][0]).abs() / (far - near)
+    P = batch["source_poses"][0].to(dev)
+    dirs = batch["ray_d"][0][:, begin:begin + k].t().to(dev)
+    pts = batch["ray_o"][0].to(dev)[None, None] + res["ref"][2][:, :, None] * dirs[:, None, :]
+    q = torch.einsum("vij,rsj->vrsi", P[:, :3, :3], pts) + P[:, None, None, :3, 3]
+    uv = q[..., :2] / q[..., 2:3]
+    amb = ((uv.abs() - 1).abs() < 2e-5).any(-1).any(0).any(1)
+    mse = float(((res["tc"][1] - res["ref"][1])[~amb] ** 2).mean())
+    return {"against": "fp32 mode of this library (1e-5 parity path) on the same rays and uniforms", "rays": int(k),
+            "depth_err_p99_frac_of_interval": float(de.quantile(0.99)), "depth_err_p50_frac_of_interval": float(de.median()),
+            "rgb_psnr_db": 10 * math.log10(1.0 / max(mse, 1e-20)), "mask_ambiguous_rays_excluded": int(amb.sum()),
+            "tolerance": {"depth_err_p99_frac_of_interval": 0.005, "rgb_psnr_db": 50.0}}
 
 
 def _ncu_traffic():
@@ -548,7 +592,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("UFO_BENCH_MODE", "tc"), choices=["fp32", "tc", "tc16"])
+    ap.add_argument("--mode", default=os.environ.get("UFO_BENCH_MODE", "tc16"), choices=["fp32", "tc", "tc16"],
+                    help="tc16 = tcgen05 with fp16 operands (default: meets the north-star tolerance at full size), tc = bf16 operands")
     ap.add_argument("--width", type=int, default=int(os.environ.get("UFO_BENCH_W", "1600")))
     ap.add_argument("--height", type=int, default=int(os.environ.get("UFO_BENCH_H", "1216")))
     ap.add_argument("--nv", type=int, default=3)

@@ -104,7 +104,7 @@ static uint16_t cvt16(float v, bool bf16) {
     __nv_bfloat16 h = __float2bfloat16_rn(v);
     return *reinterpret_cast<uint16_t*>(&h);
   }
-  __half h = __float2half_rn(v);
+  __half h = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));   // saturate like the device-side packing
   return *reinterpret_cast<uint16_t*>(&h);
 }
 static float back16(uint16_t u, bool bf16) {
