@@ -345,7 +345,7 @@ def run_b200(args):
     # ---- accuracy of this mode at THIS workload (outside every timed region): a band of rows rendered in the measured
     #      mode and in fp32 mode (the 1e-5 parity path) with the same uniforms -> the north-star tolerance figures
     accuracy = None
-    if rank == 0 and args.mode != "fp32":
+    if rank == 0 and args.mode != "fp32" and not args.no_accuracy:
         try:
             accuracy = measure_accuracy(lib, sc, weights, batch, mode, u_c, u_f, n_rays, W, H, stream)
         except Exception as ex:  # reported extra: never fail the headline line
@@ -592,6 +592,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-accuracy", action="store_true", help="skip the tensor-core vs fp32 accuracy leg (outside the timed region)")
     ap.add_argument("--mode", default=os.environ.get("UFO_BENCH_MODE", "tc16"), choices=["fp32", "tc", "tc16"],
                     help="tc16 = tcgen05 with fp16 operands (default: meets the north-star tolerance at full size), tc = bf16 operands")
     ap.add_argument("--width", type=int, default=int(os.environ.get("UFO_BENCH_W", "1600")))
