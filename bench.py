@@ -582,8 +582,27 @@ def bench_tsdf(args, dev, depth_z, sc_batch):
     # voxel and view; the reference's kernel moves (tsdf, weight) once per VIEW
     fused = upd * 16 + vox * n_views * 4
     per_view = n_views * (upd * 16) + vox * n_views * 4
-    return {"voxels": vox, "views": n_views, "updated_voxels": upd, "kernel_ms": ms, "voxel_views_per_s": vox * n_views / (ms * 1e-3),
-            "fused_gbs": fused / (ms * 1e-3) / 1e9, "reference_schedule_bytes": per_view, "hbm_peak_gbs": peaks()["hbm_gbs"]}
+    res = {"voxels": vox, "views": n_views, "updated_voxels": upd, "kernel_ms": ms, "voxel_views_per_s": vox * n_views / (ms * 1e-3),
+           "fused_gbs": fused / (ms * 1e-3) / 1e9, "reference_schedule_bytes": per_view, "hbm_peak_gbs": peaks()["hbm_gbs"]}
+    # iso-surface extraction of the fused volume on the device (ufo_tsdf_mesh_*; the reference copies the volumes to the
+    # host and runs scikit-image).  Algorithmic bytes per voxel: classify reads 4 and writes 1 (case) + 24/32 (group record
+    # and counts), the two scans and the pack move 24/32, emit reads 24/32 - 7.25 in all - plus 24 B per vertex and 12 B per
+    # face written
+    from uforecon_b200.tsdf import marching_cubes
+    v, f, n = marching_cubes(vol.device_volumes()[0])                                             # warm-up
+    nv, nf = int(v.shape[0]), int(f.shape[0])
+    del v, f, n
+    _lib.profile_begin()
+    for _ in range(3):
+        out = marching_cubes(vol.device_volumes()[0])
+        del out
+    prof = _lib.profile_end(16)
+    mesh_ms = sum(m for nme, c, m in prof if nme.startswith(("k_mc", "cub_"))) / 3
+    mesh_bytes = int(vox * 7.25) + nv * 24 + nf * 12
+    res["mesh"] = {"verts": nv, "faces": nf, "device_ms": mesh_ms, "voxels_per_s": vox / (mesh_ms * 1e-3),
+                   "algorithmic_gbs": mesh_bytes / (mesh_ms * 1e-3) / 1e9, "frac_of_hbm_peak": mesh_bytes / (mesh_ms * 1e-3) / 1e9 / peaks()["hbm_gbs"],
+                   "kernels": [{"name": nme, "launches": c, "ms": round(m / 3, 3)} for nme, c, m in prof]}
+    return res
 
 
 def main():

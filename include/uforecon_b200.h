@@ -241,6 +241,26 @@ typedef struct {
 int ufo_tsdf_integrate(const UfoTsdfGrid* grid, float* tsdf, float* weight, const UfoTsdfView* views, int32_t n_views,
                        float obs_weight, void* stream);
 
+/* Iso-surface extraction from a TSDF volume on the device ("next" row N3, second half; replaces
+ * skimage.measure.marching_cubes_lewiner(tsdf_vol, level=0) in TSDFVolume.get_mesh / get_point_cloud,
+ * tsdf_fusion.py:319-356).  Marching cubes on the cell grid: one vertex per grid edge whose end points lie on different
+ * sides of `level` (f < level = inside), placed by linear interpolation, in VOXEL coordinates like skimage's output (the
+ * caller applies verts * voxel_size + vol_origin, tsdf_fusion.py:347); unit normals from the interpolated central-
+ * difference gradient, pointing towards larger f; indexed triangles wound so that their normal points the same way.
+ * Order: vertices by owner voxel in C order then edge axis, faces by cell in C order - independent of the launch.
+ * Two calls because the sizes are data dependent:
+ *   ufo_tsdf_mesh_begin  classifies the volume, returns the counts (synchronises `stream`) and a handle that BORROWS
+ *                        `tsdf` - the volume must stay valid and unchanged until the handle is destroyed;
+ *   ufo_tsdf_mesh_emit   fills verts [n_verts,3] f32, normals [n_verts,3] f32 (may be NULL), faces [n_faces,3] i32
+ *                        (may be NULL; verts may be NULL when only faces are wanted), all [dev]; asynchronous on `stream`.
+ * scikit-image is not vendored by the reference: parity with its triangulation of ambiguous cells is unpinned; the
+ * vertex set is the same by construction (oracle/mc_oracle.py). */
+typedef struct UfoMesh UfoMesh;
+int ufo_tsdf_mesh_begin(const UfoTsdfGrid* grid, const float* tsdf, float level, UfoMesh** mesh, int64_t* n_verts,
+                        int64_t* n_faces, void* stream);
+int ufo_tsdf_mesh_emit(UfoMesh* mesh, float* verts, float* normals, int32_t* faces, void* stream);
+void ufo_tsdf_mesh_destroy(UfoMesh* mesh);
+
 /* Diagnostics: one-CTA tcgen05 GEMM through the library's own operand-staging and descriptor helpers
  * (csrc/ufo_umma.cuh).  mode 0: D[128,N] = A[128,K] . B[N,K]^T; mode 1: D = At[K,128]^T . Bt[K,N].
  * All [dev] fp32; operands are rounded to fp16 (bf16 != 0: bf16) on the way to shared memory. */

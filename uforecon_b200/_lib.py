@@ -83,7 +83,7 @@ EXPORTS = (
     "ufo_abi_version", "ufo_last_error", "ufo_device_info", "ufo_weights_create", "ufo_weights_destroy",
     "ufo_scene_create", "ufo_scene_destroy", "ufo_scene_device_bytes", "ufo_render_rays", "ufo_render_rays_host",
     "ufo_launch_count", "ufo_costvolume_stage", "ufo_debug_umma_selftest", "ufo_profile_begin", "ufo_profile_end",
-    "ufo_tsdf_integrate", "ufo_feature_grid",
+    "ufo_tsdf_integrate", "ufo_feature_grid", "ufo_tsdf_mesh_begin", "ufo_tsdf_mesh_emit", "ufo_tsdf_mesh_destroy",
 )
 
 _lib = None
@@ -127,6 +127,11 @@ def load() -> C.CDLL:
                                        C.c_void_p]
     lib.ufo_feature_grid.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(UfoMlp3), C.c_void_p,
                                      C.c_void_p]
+    lib.ufo_tsdf_mesh_begin.argtypes = [C.POINTER(UfoTsdfGrid), C.c_void_p, C.c_float, C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
+                                        C.POINTER(C.c_int64), C.c_void_p]
+    lib.ufo_tsdf_mesh_emit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ufo_tsdf_mesh_destroy.argtypes = [C.c_void_p]
+    lib.ufo_tsdf_mesh_destroy.restype = None
     lib.ufo_profile_end.argtypes = [C.POINTER(UfoProfileEntry), C.c_int32, C.POINTER(C.c_int32)]
     if lib.ufo_abi_version() != 1:
         raise UfoError(f"ABI version mismatch: library {lib.ufo_abi_version()} != binding 1")

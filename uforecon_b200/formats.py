@@ -7,6 +7,8 @@
   ``extract_geometry`` saves (code1/model.py:839-842) and ``save_tsdf`` loads (tsdf_fusion.py:459-467; it reads
   ``refview{id}.npy`` - the producer/consumer names disagree in the reference, SURVEY F14, so the name is a parameter).
 * the 8-bit previews next to them (model.py:834-836).
+* the ASCII PLY files of ``save_tsdf``: ``meshwrite`` / ``pcwrite`` (tsdf_fusion.py:384-446), same header and the same
+  ``%f`` / ``%d`` records, written in one vectorised pass instead of a Python loop per vertex.
 
 Pure numpy / PIL host code; no part of the hot path.
 """
@@ -70,3 +72,35 @@ def load_depth_result(path: str) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     """-> (depth, intrinsic, cam_pose = inv(extrinsic)) exactly as ``save_tsdf`` unpacks the file (tsdf_fusion.py:463-467)."""
     data = np.load(path, allow_pickle=True).item()
     return data["depth"], data["intrinsic"], np.linalg.inv(data["extrinsic"])
+
+
+def meshwrite(filename: str, verts: np.ndarray, faces: np.ndarray, norms: np.ndarray, colors: np.ndarray) -> None:
+    """``meshwrite`` (tsdf_fusion.py:384-417): ASCII PLY with per-vertex normal and colour, ``3 i j k`` faces."""
+    verts, norms = np.asarray(verts, dtype=np.float64), np.asarray(norms, dtype=np.float64)
+    colors, faces = np.asarray(colors).astype(np.int64), np.asarray(faces).astype(np.int64)
+    with open(filename, "w") as f:
+        f.write("ply\nformat ascii 1.0\n")
+        f.write("element vertex %d\n" % verts.shape[0])
+        f.write("property float x\nproperty float y\nproperty float z\n")
+        f.write("property float nx\nproperty float ny\nproperty float nz\n")
+        f.write("property uchar red\nproperty uchar green\nproperty uchar blue\n")
+        f.write("element face %d\n" % faces.shape[0])
+        f.write("property list uchar int vertex_index\nend_header\n")
+        if verts.shape[0]:
+            np.savetxt(f, np.hstack([verts, norms, colors]), fmt=["%f"] * 6 + ["%d"] * 3)
+        if faces.shape[0]:
+            np.savetxt(f, np.hstack([np.full((faces.shape[0], 1), 3, dtype=np.int64), faces]), fmt="%d")
+
+
+def pcwrite(filename: str, xyzrgb: np.ndarray) -> None:
+    """``pcwrite`` (tsdf_fusion.py:420-446): ASCII PLY point cloud, xyz as ``%f`` and rgb as uchar."""
+    xyzrgb = np.asarray(xyzrgb)
+    xyz = xyzrgb[:, :3].astype(np.float64)
+    rgb = xyzrgb[:, 3:].astype(np.uint8).astype(np.int64)
+    with open(filename, "w") as f:
+        f.write("ply\nformat ascii 1.0\n")
+        f.write("element vertex %d\n" % xyz.shape[0])
+        f.write("property float x\nproperty float y\nproperty float z\n")
+        f.write("property uchar red\nproperty uchar green\nproperty uchar blue\nend_header\n")
+        if xyz.shape[0]:
+            np.savetxt(f, np.hstack([xyz, rgb]), fmt=["%f"] * 3 + ["%d"] * 3)

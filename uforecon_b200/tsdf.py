@@ -2,8 +2,9 @@
 
 Same constructor arguments, attribute names and ``integrate`` / ``get_volume`` signatures as the reference class;
 volumes live on the device.  ``integrate_many`` fuses the per-view loop of ``save_tsdf`` (tsdf_fusion.py:486-502) into
-launches of up to 16 views.  Marching cubes / PLY writing stay with the reference's CPU code (skimage): they consume
-``get_volume()``.  There is no CPU fallback: without the CUDA library this module raises.
+launches of up to 16 views.  ``get_mesh`` / ``get_point_cloud`` (tsdf_fusion.py:319-356) run marching cubes on the
+device (``ufo_tsdf_mesh_*``) instead of copying the volumes to scikit-image; ``formats.meshwrite`` / ``pcwrite`` write the
+reference's PLY files.  There is no CPU fallback: without the CUDA library this module raises.
 """
 from __future__ import annotations
 
@@ -14,6 +15,35 @@ import numpy as np
 import torch
 
 from . import _lib
+
+
+def marching_cubes(volume: torch.Tensor, level: float = 0.0, normals: bool = True, faces: bool = True):
+    """``ufo_tsdf_mesh_begin`` / ``_emit`` on a device volume [X,Y,Z] fp32: (verts [Nv,3] f32 in voxel coordinates,
+    faces [Nf,3] i32 | None, normals [Nv,3] f32 | None) as device tensors - what skimage's
+    ``marching_cubes_lewiner(volume, level)`` returns, minus its ``values``."""
+    lib = _lib.load()
+    if not (volume.is_cuda and volume.dtype == torch.float32 and volume.dim() == 3):
+        raise ValueError("marching_cubes: volume must be a 3-D float32 CUDA tensor")
+    vol = volume.contiguous()
+    grid = _lib.UfoTsdfGrid()
+    grid.dim[:] = [int(x) for x in vol.shape]
+    grid.voxel_size, grid.trunc_margin = 1.0, 1.0
+    mesh = C.c_void_p()
+    nv, nf = C.c_int64(), C.c_int64()
+    with torch.cuda.device(vol.device):
+        st = torch.cuda.current_stream(vol.device)
+        _lib.check(lib.ufo_tsdf_mesh_begin(C.byref(grid), vol.data_ptr(), float(level), C.byref(mesh), C.byref(nv), C.byref(nf),
+                                           st.cuda_stream))
+        try:
+            v = torch.empty(nv.value, 3, dtype=torch.float32, device=vol.device)
+            n = torch.empty(nv.value, 3, dtype=torch.float32, device=vol.device) if normals else None
+            f = torch.empty(nf.value, 3, dtype=torch.int32, device=vol.device) if faces else None
+            _lib.check(lib.ufo_tsdf_mesh_emit(mesh, v.data_ptr(), n.data_ptr() if normals else None, f.data_ptr() if faces else None,
+                                              st.cuda_stream))
+            st.synchronize()
+        finally:
+            lib.ufo_tsdf_mesh_destroy(mesh)
+    return v, f, n
 
 
 class TSDFVolume:
@@ -71,3 +101,27 @@ class TSDFVolume:
 
     def device_volumes(self):
         return self._tsdf_vol, self._weight_vol
+
+    def extract_surface(self, level: float = 0.0, normals: bool = True, faces: bool = True):
+        """Marching cubes of the fused volume on the device, see :func:`marching_cubes`."""
+        return marching_cubes(self._tsdf_vol, level, normals, faces)
+
+    def _vertex_colors(self, verts_vox: torch.Tensor) -> np.ndarray:
+        # tsdf_fusion.py:346-354 decode color_vol at round(verts); the reference's kernel never writes color_vol
+        # (`return` before the colour branch, :137), so every decoded colour is 0
+        return np.zeros((verts_vox.shape[0], 3), dtype=np.uint8)
+
+    def get_mesh(self):
+        """``TSDFVolume.get_mesh`` (tsdf_fusion.py:340-356): (verts [Nv,3] world, faces [Nf,3], norms [Nv,3], colors
+        [Nv,3] uint8) as numpy arrays."""
+        v, f, n = self.extract_surface()
+        origin = torch.from_numpy(self._vol_origin).to(self.device)
+        verts = v * self._voxel_size + origin                                       # :347
+        return verts.cpu().numpy(), f.cpu().numpy(), n.cpu().numpy(), self._vertex_colors(v)
+
+    def get_point_cloud(self):
+        """``TSDFVolume.get_point_cloud`` (tsdf_fusion.py:319-338): [Nv, 6] = xyz (world) | rgb."""
+        v, _, _ = self.extract_surface(normals=False, faces=False)
+        origin = torch.from_numpy(self._vol_origin).to(self.device)
+        verts = (v * self._voxel_size + origin).cpu().numpy()
+        return np.hstack([verts, self._vertex_colors(v).astype(verts.dtype)])
