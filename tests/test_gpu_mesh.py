@@ -18,12 +18,15 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 def _volumes():
     rng = np.random.default_rng(3)
     out = {}
-    for shape in ((9, 8, 10), (33, 17, 40), (2, 2, 2), (6, 1, 6), (1, 1, 5)):
+    # rows shorter than, equal to and longer than one 32-voxel group; single planes and single rows
+    for shape in ((9, 8, 10), (33, 17, 40), (2, 2, 2), (6, 1, 6), (1, 1, 5), (5, 7, 132), (3, 3, 4), (6, 5, 256), (4, 1, 8)):
         vol = rng.standard_normal(shape).astype(np.float32)
         vol[rng.random(shape) < 0.05] = 0.0
         out["noise" + "x".join(map(str, shape))] = vol
     g = np.mgrid[0:70, 0:64, 0:61].astype(np.float32)
     out["sphere"] = (np.sqrt(((g - 30.3) ** 2).sum(0)) - 21.7).astype(np.float32)
+    g = np.mgrid[0:40, 0:44, 0:160].astype(np.float32)
+    out["sphere4"] = (np.sqrt(((g - np.array([19.2, 21.1, 80.4], np.float32)[:, None, None, None]) ** 2).sum(0)) - 17.3).astype(np.float32)
     out["empty"] = np.ones((8, 8, 8), dtype=np.float32)
     return out
 
@@ -32,7 +35,7 @@ def _volumes():
 def test_mesh_bit_exact_vs_oracle(name):
     from uforecon_b200.tsdf import marching_cubes
     vol = _volumes()[name]
-    level = 0.0 if name != "sphere" else 0.25
+    level = 0.0 if not name.startswith("sphere") else 0.25
     v0, f0, n0 = mc.marching_cubes(vol, level)
     v, f, n = marching_cubes(torch.from_numpy(vol).cuda(), level)
     assert tuple(v.shape) == v0.shape and tuple(f.shape) == f0.shape
