@@ -55,3 +55,15 @@ def test_depth_result_round_trip(tmp_path):
     png = np.array(Image.open(tmp_path / "scan24" / "depth" / "00000003.png"))
     assert png.shape == (12, 16) and png.max() == 255
     assert np.array(Image.open(tmp_path / "rgb" / "scan24" / "00000003.jpg")).shape == (12, 16, 3)
+
+
+def test_pair_file_roundtrip_and_reference_layout(tmp_path):
+    """the two-lines-per-viewpoint layout of dtu_pairs.txt (dtu_train.py:171-178), incl. the trailing blank of each line"""
+    p = tmp_path / "pair.txt"
+    p.write_text("3\n0\n3 10 2346.410000 1 2036.530000 9 1243.890000 \n1\n2 9 2850.870000 10 2583.940000 \n7\n0 \n")
+    pairs = formats.read_pair_file(str(p))
+    assert pairs == {0: [10, 1, 9], 1: [9, 10], 7: []}
+    q = tmp_path / "pair2.txt"
+    formats.write_pair_file(str(q), pairs, {0: [2346.41, 2036.53, 1243.89], 1: [2850.87, 2583.94], 7: []})
+    assert formats.read_pair_file(str(q)) == pairs
+    assert q.read_text().splitlines()[2] == "3 10 2346.410000 1 2036.530000 9 1243.890000 "

@@ -3,6 +3,8 @@
 * DTU ``cameras/%08d_cam.txt``: read/write in the layout ``DtuFitSparse.read_cam_file`` parses
   (code1/dataset/dtu_test_sparse.py:184-206; README.md:67-81 of the reference): line 0 ``extrinsic``, lines 1-4 the
   4x4 world-to-camera matrix, line 6 ``intrinsic``, lines 7-9 the 3x3 K, line 11 ``DEPTH_MIN DEPTH_INTERVAL``.
+* the MVSNet view-pair list ``dtu_pairs.txt`` (``MVSDataset.build_metas``, code1/dataset/dtu_train.py:171-178): first line
+  the number of viewpoints, then per viewpoint one line with its id and one line ``N id score id score ...``.
 * depth-map results: ``depth/<scan>/<view>.npy`` holding the pickled dict ``{"depth", "extrinsic", "intrinsic"}`` that
   ``extract_geometry`` saves (code1/model.py:839-842) and ``save_tsdf`` loads (tsdf_fusion.py:459-467; it reads
   ``refview{id}.npy`` - the producer/consumer names disagree in the reference, SURVEY F14, so the name is a parameter).
@@ -46,6 +48,27 @@ def write_cam_file(filename: str, extrinsic: np.ndarray, intrinsic: np.ndarray, 
         for r in np.asarray(intrinsic, dtype=np.float64).reshape(3, 3):
             f.write(" ".join(repr(float(np.float32(x))) for x in r) + "\n")
         f.write(f"\n{depth_min} {depth_interval}\n")
+
+
+def read_pair_file(filename: str) -> Dict[int, list]:
+    """``ref_src_pairs`` of ``build_metas`` (dtu_train.py:171-178): reference view -> source views, best first (the scores
+    at the odd positions of the line are dropped exactly like the reference's ``split()[1::2]``)."""
+    pairs: Dict[int, list] = {}
+    with open(filename) as f:
+        n = int(f.readline())
+        for _ in range(n):
+            ref = int(f.readline().rstrip())
+            pairs[ref] = [int(x) for x in f.readline().rstrip().split()[1::2]]
+    return pairs
+
+
+def write_pair_file(filename: str, pairs: Dict[int, list], scores: Dict[int, list] = None) -> None:
+    """Inverse of :func:`read_pair_file` (scores default to 0)."""
+    with open(filename, "w") as f:
+        f.write("%d\n" % len(pairs))
+        for ref, srcs in pairs.items():
+            sc = scores[ref] if scores is not None else [0.0] * len(srcs)
+            f.write("%d\n%d " % (ref, len(srcs)) + " ".join("%d %f" % (s, c) for s, c in zip(srcs, sc)) + " \n")
 
 
 def save_depth_result(out_dir: str, scan: str, view: str, depth_mm: np.ndarray, rgb: np.ndarray, extrinsic: np.ndarray,
