@@ -67,6 +67,21 @@ static int check_device() {
   return UFO_OK;
 }
 
+// Stream-ordered temporaries of one call: released (cudaFreeAsync) on every return path.
+namespace {
+struct AsyncTemps {
+  cudaStream_t st;
+  std::vector<void*> ptrs;
+  explicit AsyncTemps(cudaStream_t s) : st(s) {}
+  ~AsyncTemps() { for (void* p : ptrs) cudaFreeAsync(p, st); }
+  int alloc(void** out, size_t bytes) {
+    UFO_CUDA(cudaMallocAsync(out, bytes, st));
+    ptrs.push_back(*out);
+    return UFO_OK;
+  }
+};
+}  // namespace
+
 extern "C" int ufo_abi_version(void) { return UFO_ABI_VERSION; }
 extern "C" const char* ufo_last_error(void) { return g_err; }
 extern "C" int64_t ufo_launch_count(void) { return (int64_t)g_launches.load(); }
@@ -205,6 +220,10 @@ extern "C" int ufo_weights_create(const UfoWeightsDesc* d, UfoWeights** out, voi
   if (!d->view_token || !d->depth_freqs || !d->depth_phases) return fail(UFO_EINVAL, "ufo_weights_create: missing tensor");
 
   UfoWeights* w = new UfoWeights();
+  struct Guard {                 // frees the handle on every early return below
+    UfoWeights* w;
+    ~Guard() { if (w) ufo_weights_destroy(w); }
+  } guard{w};
   UFO_CUDA(cudaGetDevice(&w->device));
   BlobBuilder b;
   size_t off[64];
@@ -278,10 +297,8 @@ extern "C" int ufo_weights_create(const UfoWeightsDesc* d, UfoWeights** out, voi
   w->pe_table = w->blob + off[k++];
   // SingleVarianceNetwork: exp(10*variance) clipped to [1e-6, 1e6] (single_variance_network.py:11, renderer.py:25)
   w->inv_s = fminf(fmaxf(expf(d->variance * 10.0f), 1e-6f), 1e6f);
-  if (int e = tc_weights_build(d, &w->tc, stream)) {
-    ufo_weights_destroy(w);
-    return e;
-  }
+  if (int e = tc_weights_build(d, &w->tc, stream)) return e;
+  guard.w = nullptr;
   *out = w;
   return UFO_OK;
 }
@@ -317,6 +334,10 @@ extern "C" int ufo_scene_create(const UfoSceneDesc* d, UfoScene** out, void* str
       return fail(UFO_EINVAL, "ufo_scene_create: bad volume %d", s);
   cudaStream_t st = (cudaStream_t)stream_;
   UfoScene* sc = new UfoScene();
+  struct Guard {                 // every early return below (the UFO_CUDA / UFO_KERNEL macros included) frees the scene
+    UfoScene* s;
+    ~Guard() { if (s) ufo_scene_destroy(s); }
+  } guard{sc};
   UFO_CUDA(cudaGetDevice(&sc->device));
   SceneDev& D = sc->d;
   const int nv = d->n_views;
@@ -330,41 +351,40 @@ extern "C" int ufo_scene_create(const UfoSceneDesc* d, UfoScene** out, void* str
   int e;
   const long long hw = (long long)D.h * D.w, HW = (long long)D.H * D.W;
   float* feat_cl; float4* rgbd; float* match_cl;
-  if ((e = dalloc(sizeof(float) * nv * hw * kFeatC, (void**)&feat_cl))) { ufo_scene_destroy(sc); return e; }
-  if ((e = dalloc(sizeof(float4) * nv * HW, (void**)&rgbd))) { ufo_scene_destroy(sc); return e; }
-  if ((e = dalloc(sizeof(float) * nv * (nv - 1) * hw * kFeatC, (void**)&match_cl))) { ufo_scene_destroy(sc); return e; }
-  if ((e = repack_cl<kFeatC>(d->img_feats, feat_cl, hw, nv, st))) { ufo_scene_destroy(sc); return e; }
-  if ((e = repack_cl<kFeatC>(d->match_feats, match_cl, hw, nv * (nv - 1), st))) { ufo_scene_destroy(sc); return e; }
+  if ((e = dalloc(sizeof(float) * nv * hw * kFeatC, (void**)&feat_cl))) return e;
+  if ((e = dalloc(sizeof(float4) * nv * HW, (void**)&rgbd))) return e;
+  if ((e = dalloc(sizeof(float) * nv * (nv - 1) * hw * kFeatC, (void**)&match_cl))) return e;
+  if ((e = repack_cl<kFeatC>(d->img_feats, feat_cl, hw, nv, st))) return e;
+  if ((e = repack_cl<kFeatC>(d->match_feats, match_cl, hw, nv * (nv - 1), st))) return e;
   UFO_KERNEL("k_pack_rgbd", st, k_pack_rgbd<<<cdiv(HW * nv, 256), 256, 0, st>>>(d->source_imgs, d->depth_info, rgbd, HW, nv));
   D.feat_cl = feat_cl; D.rgbd_cl = rgbd; D.match_cl = match_cl;
   {  // the reference stores every pair map twice; when the two copies are bit-identical both samples of a
      // pair read the same copy, which halves the working set of the dominant gather at large NV
-    int* flag = nullptr;
-    UFO_CUDA(cudaMalloc(&flag, sizeof(int)));
+    int* flag = nullptr;           // owned by the scene (4 bytes), so that no return path can leak it
+    if ((e = dalloc(sizeof(int), (void**)&flag))) return e;
     UFO_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
     UFO_KERNEL("k_match_sym_check", st, k_match_sym_check<<<dim3(64, nv, nv), 256, 0, st>>>(d->match_feats, nv, hw, flag));
     int differ = 1;
     cudaError_t ce = cudaMemcpyAsync(&differ, flag, sizeof(int), cudaMemcpyDeviceToHost, st);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
-    cudaFree(flag);
-    if (ce != cudaSuccess) { ufo_scene_destroy(sc); return fail(UFO_ECUDA, "ufo_scene_create: %s", cudaGetErrorString(ce)); }
+    if (ce != cudaSuccess) { return fail(UFO_ECUDA, "ufo_scene_create: %s", cudaGetErrorString(ce)); }
     D.match_sym = differ ? 0 : 1;
   }
   for (int s = 0; s < 3; ++s) {
     D.vd[s] = d->vol_d[s]; D.vh[s] = d->vol_h[s]; D.vw[s] = d->vol_w[s];
     const long long vox = (long long)D.vd[s] * D.vh[s] * D.vw[s];
     float* vf;
-    if ((e = dalloc(sizeof(float) * nv * vox * kVolC, (void**)&vf))) { ufo_scene_destroy(sc); return e; }
-    if ((e = repack_cl<kVolC>(d->vol_feat[s], vf, vox, nv, st))) { ufo_scene_destroy(sc); return e; }
+    if ((e = dalloc(sizeof(float) * nv * vox * kVolC, (void**)&vf))) return e;
+    if ((e = repack_cl<kVolC>(d->vol_feat[s], vf, vox, nv, st))) return e;
     D.vol_feat_cl[s] = vf;
     float* vw;  // single channel: layout already [NV][D][h][w]; copied so the scene owns its inputs
-    if ((e = dalloc(sizeof(float) * nv * vox, (void**)&vw))) { ufo_scene_destroy(sc); return e; }
+    if ((e = dalloc(sizeof(float) * nv * vox, (void**)&vw))) return e;
     UFO_CUDA(cudaMemcpyAsync(vw, d->vol_weight[s], sizeof(float) * nv * vox, cudaMemcpyDeviceToDevice, st));
     D.vol_w[s] = vw;
   }
   float *rd, *crd;
-  if ((e = dalloc(sizeof(float) * 3 * HW, (void**)&rd))) { ufo_scene_destroy(sc); return e; }
-  if ((e = dalloc(sizeof(float) * 3 * HW, (void**)&crd))) { ufo_scene_destroy(sc); return e; }
+  if ((e = dalloc(sizeof(float) * 3 * HW, (void**)&rd))) return e;
+  if ((e = dalloc(sizeof(float) * 3 * HW, (void**)&crd))) return e;
   UFO_CUDA(cudaMemcpyAsync(rd, d->ray_d, sizeof(float) * 3 * HW, cudaMemcpyDeviceToDevice, st));
   UFO_CUDA(cudaMemcpyAsync(crd, d->cam_ray_d, sizeof(float) * 3 * HW, cudaMemcpyDeviceToDevice, st));
   D.ray_d = rd; D.cam_ray_d = crd;
@@ -379,6 +399,7 @@ extern "C" int ufo_scene_create(const UfoSceneDesc* d, UfoScene** out, void* str
   }
   D.near0 = d->near_fars[0];
   D.far0 = d->near_fars[1];
+  guard.s = nullptr;
   *out = sc;
   return UFO_OK;
 }
@@ -861,10 +882,11 @@ extern "C" int ufo_costvolume_stage(const float* const* feats, int32_t N, int32_
   float* cl = nullptr;          // V channel-last copies
   WarpMats* mats_dev = nullptr;
   const float** src_ptrs_dev = nullptr;
-  UFO_CUDA(cudaMallocAsync((void**)&cl, sizeof(float) * fl * V, st));
-  UFO_CUDA(cudaMallocAsync((void**)&mats_dev, sizeof(WarpMats) * mats.size(), st));
-  UFO_CUDA(cudaMallocAsync((void**)&src_ptrs_dev, sizeof(float*) * (V - 1), st));
+  AsyncTemps tmp(st);
   int e = UFO_OK;
+  if ((e = tmp.alloc((void**)&cl, sizeof(float) * fl * V))) return e;
+  if ((e = tmp.alloc((void**)&mats_dev, sizeof(WarpMats) * mats.size()))) return e;
+  if ((e = tmp.alloc((void**)&src_ptrs_dev, sizeof(float*) * (V - 1)))) return e;
   for (int i = 0; i < V && !e; ++i) {
     if (C == 32) e = repack_cl<32>(feats[i], cl + fl * i, (long long)h * w, N, st);
     else if (C == 16) e = repack_cl<16>(feats[i], cl + fl * i, (long long)h * w, N, st);
@@ -883,9 +905,6 @@ extern "C" int ufo_costvolume_stage(const float* const* feats, int32_t N, int32_
     else if (C == 16) e = launch_costvol<16, 32>(cl, src_ptrs_dev, mats_dev, hyp, vw_in, pw, N, V, h, w, sim, vw_out, st);
     else e = launch_costvol<8, 8>(cl, src_ptrs_dev, mats_dev, hyp, vw_in, pw, N, V, h, w, sim, vw_out, st);
   }
-  cudaFreeAsync(cl, st);
-  cudaFreeAsync(mats_dev, st);
-  cudaFreeAsync((void*)src_ptrs_dev, st);
   return e;
 }
 
@@ -911,9 +930,11 @@ extern "C" int ufo_feature_grid(const float* feats, int32_t nv, int32_t h, int32
   wts.insert(wts.end(), lin->b4, lin->b4 + 8);
   float *cl = nullptr, *wd = nullptr;
   const size_t fl = (size_t)nv * kFeatC * h * w;
-  UFO_CUDA(cudaMallocAsync((void**)&cl, sizeof(float) * fl, st));
-  UFO_CUDA(cudaMallocAsync((void**)&wd, sizeof(float) * wts.size(), st));
-  int e = repack_cl<kFeatC>(feats, cl, (long long)h * w, nv, st);
+  AsyncTemps tmp(st);
+  int e = UFO_OK;
+  if ((e = tmp.alloc((void**)&cl, sizeof(float) * fl))) return e;
+  if ((e = tmp.alloc((void**)&wd, sizeof(float) * wts.size()))) return e;
+  e = repack_cl<kFeatC>(feats, cl, (long long)h * w, nv, st);
   if (!e) {
     cudaError_t ce = cudaMemcpyAsync(wd, wts.data(), sizeof(float) * wts.size(), cudaMemcpyHostToDevice, st);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);     // host vector goes out of scope below
@@ -921,15 +942,11 @@ extern "C" int ufo_feature_grid(const float* feats, int32_t nv, int32_t h, int32
   }
   if (!e) {
     const long long total = (long long)reso * reso * reso;
-    [&]() -> int {
+    e = [&]() -> int {
       UFO_KERNEL("k_feature_grid", st, k_feature_grid<<<cdiv(total, 128), 128, 0, st>>>(cl, h, w, reso, V, wd, out));
       return UFO_OK;
     }();
-    cudaError_t ce = cudaGetLastError();
-    if (ce != cudaSuccess) e = fail(UFO_ECUDA, "ufo_feature_grid: %s", cudaGetErrorString(ce));
   }
-  cudaFreeAsync(cl, st);
-  cudaFreeAsync(wd, st);
   return e;
 }
 
