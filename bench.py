@@ -459,7 +459,8 @@ def measure_accuracy(lib, sc, weights, batch, mode, u_c, u_f, n_rays, W, H, stre
 
 
 def _ncu_traffic():
-    """dram bytes per launch from the committed ncu --set full capture (profiles/ncu_traffic.json), or {}."""
+    """DRAM bytes per sample point of the dominant kernels from the committed ncu --set full capture
+    (profiles/ncu_traffic.json), or {}; scaled to this run's average launch in roofline_entries."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     return json.load(open(p)) if os.path.exists(p) else {}
 
@@ -499,7 +500,8 @@ def roofline_entries(prof, args, n_rays, pk):
         achieved = per_launch / avg_s / (1e12 if bound == "tensor" else 1e9)
         peak = pk["tf_sustained"] if bound == "tensor" else pk["hbm_gbs"]
         e = {"kernel": name, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
-             "traffic": traffic.get(name.split("<")[0]),
+             "traffic": (traffic[name.split("<")[0]]["bytes_per_point"] * (pts_ray if name.startswith("k_ray_tc") else pts_pt) / cnt
+                         if isinstance(traffic.get(name.split("<")[0]), dict) else None),
              "peak_source": pk["src"] + (" (sustained bf16)" if bound == "tensor" else " (copy)"),
              "launches": cnt, "avg_launch_ms": avg_s * 1e3, "share_of_step": ms / total_ms,
              "algorithmic_work_per_launch": per_launch,

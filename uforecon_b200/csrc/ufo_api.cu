@@ -56,7 +56,7 @@ using namespace ufo;
 // handles
 // ------------------------------------------------------------------------------------------------
 static int fp32_chunk_rays();
-static int tc_chunk_rays(int sms);
+static int tc_chunk_rays(int sms, int nv);
 
 static int check_device() {
   int n = 0;
@@ -581,10 +581,19 @@ static int render_chunk_fp32(const UfoScene* sc, const UfoWeights* w, const int6
 // ------------------------------------------------------------------------------------------------
 // tensor-core pipeline
 // ------------------------------------------------------------------------------------------------
-static int tc_chunk_rays(int sms) {
-  const char* e = getenv("UFO_TC_CHUNK");
-  int v = e ? atoi(e) : sms * 64;   // fine pass: 64 ray tiles per CTA; fewer launches and weight reloads per ray
-  return v < 2 ? 2 : v;
+static int tc_chunk_rays(int sms, int nv) {
+  // Rays per pass of the tensor-core pipeline.  Larger chunks mean fewer launches and shorter kernel tails: measured on a
+  // B200 at 1600x1216, NV=3 (ms per depth map) 64 tiles per CTA 891, 96: 875, 128: 873, 192: 870, 256: 865.  The per-chunk
+  // workspace (tws_ensure: ~123 KB per ray at NV=3, ~294 KB at NV=10) is capped at 8 GiB.
+  if (const char* e = getenv("UFO_TC_CHUNK")) {
+    const int v = atoi(e);
+    return v < 2 ? 2 : v;
+  }
+  const size_t per_ray = (size_t)kNS * (kDView * 4 + 8 + (size_t)nv * (kDView * 2 + 32) + 16 + 32 + 1) + 32 + 2 * kNC * 4;
+  const long long cap = (long long)((8ull << 30) / per_ray);
+  long long v = (long long)sms * 256;
+  if (v > cap) v = cap / sms * sms;
+  return v < sms ? sms : (int)v;
 }
 
 static int tws_ensure(const UfoScene* sc, int rays) {
@@ -712,7 +721,7 @@ extern "C" int ufo_render_rays(const UfoScene* sc, const UfoWeights* w, const in
     int cc_major = 0;
     UFO_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
     if (cc_major != 10) return fail(UFO_ENODEVICE, "ufo_render_rays: the tensor-core modes need an sm_100 device (tcgen05), found sm_%d", cc_major * 10);
-    const int chunk = tc_chunk_rays(sms);
+    const int chunk = tc_chunk_rays(sms, sc->d.nv);
     if (int e = tws_ensure(sc, n_rays < chunk ? n_rays : chunk)) return e;
     for (int64_t off = 0; off < n_rays; off += chunk) {
       const int R = (int)((n_rays - off) < chunk ? (n_rays - off) : chunk);
@@ -762,7 +771,7 @@ extern "C" int ufo_render_rays_host(const UfoScene* sc, const UfoWeights* w, int
   int sms = 0, dev = 0;
   UFO_CUDA(cudaGetDevice(&dev));
   UFO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int64_t block = (int64_t)(mode == UFO_MODE_FP32 ? fp32_chunk_rays() : tc_chunk_rays(sms)) * 4;
+  const int64_t block = (int64_t)(mode == UFO_MODE_FP32 ? fp32_chunk_rays() : tc_chunk_rays(sms, sc->d.nv)) * 4;
   const size_t pitch = sizeof(float) * (size_t)n_rays;
   int k = 0;
   for (int64_t off = 0; off < n_rays; off += block, ++k) {
