@@ -52,7 +52,9 @@ enum {
 enum {
   UFO_MODE_FP32 = 0, /* CUDA-core fp32 everywhere (parity: 1e-5 relative)                        */
   UFO_MODE_TC = 1,   /* BF16 operands / FP32 accumulate on tcgen05 tensor cores for the GEMMs    */
-  UFO_MODE_TC_F16 = 2 /* same kernels with FP16 operands (3 more mantissa bits, narrower range)  */
+  UFO_MODE_TC_F16 = 2 /* same kernels with FP16 operands (3 more mantissa bits; packing saturates at
+                       * +-65504).  The recommended mode: inside the tolerance (p99 depth error <= 0.5 % of the
+                       * interval, PSNR >= 50 dB) at 1600x1216, where BF16 operands are not.          */
 };
 
 typedef struct UfoScene UfoScene;     /* one view set: repacked source tensors + cameras        */
@@ -159,7 +161,7 @@ int64_t ufo_scene_device_bytes(const UfoScene* s);
  *   u_coarse  [dev] [64, u_stride]  uniforms of FixedSampler's jitter, column i <-> ray i
  *   u_fine    [dev] [64, u_stride]  uniforms of ImportanceSampler (reference draws [64,RN] and
  *             transposes, sampler.py:86); u_stride >= n_rays is the row pitch in floats
- *   mode      UFO_MODE_FP32 | UFO_MODE_TC
+ *   mode      UFO_MODE_FP32 | UFO_MODE_TC | UFO_MODE_TC_F16
  */
 int ufo_render_rays(const UfoScene* scene, const UfoWeights* weights, const int64_t* ray_idx,
                     int64_t ray_begin, int32_t n_rays, const float* u_coarse, const float* u_fine,
