@@ -20,8 +20,9 @@ views, unfavourable set 1/16/36, 64+64 samples per ray) rendered by ``ufo_render
   ``sec_per_depth_map_sharded`` additionally times ONE depth map with its rows sharded over the N ranks
   (configs[2]) including the gather of depth/rgb to rank 0.
 
-``--impl reference`` times the reference's CPU implementation of the same path on the host cores (the
-oracle port - /root/reference does not exist on the GPU box) and prints the same JSON line shape.
+``--impl reference`` times the reference's own CPU implementation of the same path on the host cores - the UNMODIFIED
+reference staged under baseline/_ref by ``baseline/reference_arm.py`` (the oracle port only if that copy is absent) - and
+prints the same JSON line shape.  ``reference_cuda`` (N=1 extra) times the same unmodified call with model and scene on cuda:0.
 """
 from __future__ import annotations
 
@@ -156,10 +157,22 @@ def peaks():
 # --------------------------------------------------------------------------------------------------
 # CPU leg (oracle port of the reference) - used by cpu_baseline and by --impl reference
 # --------------------------------------------------------------------------------------------------
+_REF_MODELS = {}
+
+
 def cpu_chunks(batch, scene, sd, n_chunks: int, chunk: int = 800, warm: int = 1):
-    """Times ``n_chunks`` calls of the reference's ``infer`` restatement on ``chunk`` rays each (the reference's
-    own chunking: --test_ray_num 800, script/eval_dtu_unfavorable.sh).  Returns (rays/s, seconds, rays)."""
-    from oracle import uforecon_oracle as orc      # checker / CPU baseline only
+    """Times ``n_chunks`` calls of the reference's ``infer`` on ``chunk`` rays each (the reference's own chunking:
+    --test_ray_num 800, script/eval_dtu_unfavorable.sh) on the host cores.  Runs the UNMODIFIED reference staged under
+    baseline/_ref (``kind`` "reference"); only when that copy is absent, the oracle restatement (``kind`` "port").
+    Returns (rays/s, seconds, rays, kind)."""
+    from baseline import reference_arm
+    if reference_arm.available():
+        nv = batch["source_imgs"].shape[1]
+        if nv not in _REF_MODELS:
+            _REF_MODELS[nv] = reference_arm.load_model(nv, sd, "cpu")
+        v, secs, rays, _ = reference_arm.infer_chunks(_REF_MODELS[nv], batch, scene, n_chunks, chunk, warm, "cpu")
+        return v, secs, rays, "reference"
+    from oracle import uforecon_oracle as orc      # CPU baseline only, never the product path
     from uforecon_b200 import synthetic
     H, W = batch["source_imgs"].shape[-2:]
     total = H * W
@@ -177,11 +190,44 @@ def cpu_chunks(batch, scene, sd, n_chunks: int, chunk: int = 800, warm: int = 1)
                 times.append((dt, len(ray_idx)))
     secs = sum(t for t, _ in times)
     rays = sum(n for _, n in times)
-    return rays / secs, secs, rays
+    return rays / secs, secs, rays, "port"
+
+
+def reference_on_cuda(batch, scene, sd, dev, chunks=(800, 4000, 16000), n_chunks=3):
+    """Same-device bar: the UNMODIFIED reference's ``UFORecon.infer`` with the model and the scene
+    tensors on the B200 - its ATen / cuBLAS op sequence - per chunk size, TF32 off (torch 1.13 default) and on."""
+    from baseline import reference_arm
+    if not reference_arm.available():
+        return {"unavailable": "baseline/_ref not staged"}
+    nv = batch["source_imgs"].shape[1]
+    model = reference_arm.load_model(nv, sd, dev)
+    b = reference_arm.to_device(batch, dev)
+    s = reference_arm.to_device(scene, dev)
+    H, W = batch["source_imgs"].shape[-2:]
+    rows = []
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    try:
+        for tf32 in (False, True):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            for ch in chunks:
+                try:
+                    v, secs, rays, _ = reference_arm.infer_chunks(model, b, s, n_chunks, ch, 1, dev)
+                    rows.append({"chunk_rays": ch, "tf32": tf32, "rays_per_s": v, "sec_per_depth_map": H * W / v, "rays_timed": rays})
+                except torch.OutOfMemoryError:
+                    rows.append({"chunk_rays": ch, "tf32": tf32, "error": "out of memory"})
+                    torch.cuda.empty_cache()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    del model, b, s
+    torch.cuda.empty_cache()
+    return {"what": "unmodified reference UFORecon.infer (code1/model.py:393-478) with model + scene on cuda:0, "
+                    "wall clock around each call with synchronize, sampler uniforms drawn on the CPU as the reference does",
+            "rows": rows, "best_rays_per_s": max((r.get("rays_per_s", 0.0) for r in rows), default=0.0)}
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation (oracle port) on all host threads."""
+    """--impl reference: the reference's own CPU implementation (baseline/_ref, unmodified) on all host threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -192,9 +238,9 @@ def run_reference(args):
     # warm-up steps and timed steps are both bounded samples (per_step chunks of 800 rays)
     for _ in range(min(args.warmup, 1)):
         cpu_chunks(batch, scene, sd, 1, chunk, warm=0)
-    t_all, r_all = 0.0, 0
+    t_all, r_all, kind = 0.0, 0, "port"
     for _ in range(args.steps):
-        _, secs, rays = cpu_chunks(batch, scene, sd, per_step, chunk, warm=0)
+        _, secs, rays, kind = cpu_chunks(batch, scene, sd, per_step, chunk, warm=0)
         t_all += secs
         r_all += rays
     val = r_all / t_all
@@ -205,9 +251,11 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "sec_per_depth_map": H * W / val,
         "config": workload_config(args, views, src, "cpu-fp32"),
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
                          "sample": f"{args.steps} steps x {per_step} chunks of {chunk} rays of the same workload "
-                                   f"(reference chunking --test_ray_num 800), extrapolated"},
+                                   f"(reference chunking --test_ray_num 800), extrapolated; "
+                                   + ("unmodified reference staged under baseline/_ref" if kind == "reference"
+                                      else "oracle restatement (baseline/_ref absent)")},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -388,11 +436,19 @@ def run_b200(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
-        v, secs, rays = cpu_chunks(batch, scene, sd, args.cpu_chunks)
-        cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+        v, secs, rays, kind = cpu_chunks(batch, scene, sd, args.cpu_chunks)
+        cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
                "sample": f"{args.cpu_chunks} chunks of 800 rays of the same workload after 1 warm-up chunk "
-                         f"({secs:.1f} s of CPU work, oracle restatement of the reference, torch CPU fp32)",
+                         f"({secs:.1f} s of CPU work, "
+                         + ("unmodified reference UFORecon.infer from baseline/_ref" if kind == "reference" else "oracle restatement of the reference")
+                         + ", torch CPU fp32)",
                "sec_per_depth_map_extrapolated": n_rays / v}
+    ref_cuda = None
+    if rank == 0 and world == 1 and not args.no_ref_cuda:
+        try:
+            ref_cuda = reference_on_cuda(batch, scene, sd, dev)
+        except Exception as ex:  # reported extra: never fail the headline line
+            ref_cuda = {"error": repr(ex)}
 
     if rank == 0:
         line = {
@@ -415,6 +471,7 @@ def run_b200(args):
             "profiled_ms_per_step": ms_prof_total / args.steps,
             "kernels": [{"name": n, "launches": c, "ms": round(ms, 3)} for n, c, ms in sorted(prof, key=lambda x: -x[2])[:12]],
             "cpu_baseline": cpu,
+            "reference_cuda": ref_cuda,
             "setup_s": round(setup_s, 1),
             "scene_device_bytes": sc.device_bytes,
         }
@@ -625,6 +682,7 @@ def main():
     ap.add_argument("--ref-chunks", type=int, default=2, help="--impl reference: 800-ray chunks per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-costvolume", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip the same-device extra (unmodified reference on cuda:0)")
     ap.add_argument("--rays", type=int, default=0, help="profiling aid: render only the first N rays of the map per step")
     args = ap.parse_args()
     if args.impl == "reference":

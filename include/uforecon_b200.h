@@ -264,7 +264,8 @@ int ufo_tsdf_mesh_emit(UfoMesh* mesh, float* verts, float* normals, int32_t* fac
 void ufo_tsdf_mesh_destroy(UfoMesh* mesh);
 
 /* Diagnostics: one-CTA tcgen05 GEMM through the library's own operand-staging and descriptor helpers
- * (csrc/ufo_umma.cuh).  mode 0: D[128,N] = A[128,K] . B[N,K]^T; mode 1: D = At[K,128]^T . Bt[K,N].
+ * (csrc/ufo_umma.cuh).  mode 0: D[128,N] = A[128,K] . B[N,K]^T; mode 1: D = At[K,128]^T . Bt[K,N];
+ * mode 2: two independent halves of one CTA, A operand in TMEM: D[2,128,N] = A[2,128,K] . B[N,K]^T (N<=160, K<=176).
  * All [dev] fp32; operands are rounded to fp16 (bf16 != 0: bf16) on the way to shared memory. */
 int ufo_debug_umma_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t mode,
                             int32_t bf16, void* stream);

@@ -29,3 +29,22 @@ def test_umma_gemm(mode, N, K, bf16):
     torch.cuda.synchronize()
     err = (D.cpu().double() - ref).abs().max().item()
     assert err < 1e-3 * (K ** 0.5), f"max err {err}"
+
+
+@pytest.mark.parametrize("bf16", [0, 1])
+@pytest.mark.parametrize("N,K", [(80, 80), (160, 80), (80, 160), (16, 96), (96, 176), (160, 176)])
+def test_umma_gemm_ts_two_halves(N, K, bf16):
+    """A operand written to TMEM by its row owners (tcgen05.st), two halves of one CTA issuing independently."""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(N * 1000 + K + 7)
+    dt = torch.bfloat16 if bf16 else torch.float16
+    A = torch.randn(2, 128, K, generator=g)
+    B = torch.randn(N, K, generator=g)
+    ref = A.to(dt).double() @ B.to(dt).double().t()
+    Ad, Bd = A.cuda().contiguous(), B.cuda().contiguous()
+    D = torch.full((2, 128, N), float("nan"), device="cuda")
+    _lib.check(lib.ufo_debug_umma_selftest(Ad.data_ptr(), Bd.data_ptr(), D.data_ptr(), N, K, 2, bf16,
+                                           torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    err = (D.cpu().double() - ref).abs().max().item()
+    assert err < 1e-3 * (K ** 0.5), f"max err {err}"

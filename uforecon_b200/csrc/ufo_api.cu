@@ -1045,11 +1045,22 @@ extern "C" int ufo_profile_end(UfoProfileEntry* out, int32_t cap, int32_t* n_out
 extern "C" int ufo_debug_umma_selftest(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t mode, int32_t bf16,
                                        void* stream_) {
   if (!A || !B || !D) return fail(UFO_EINVAL, "ufo_debug_umma_selftest: null argument");
-  if (N < 16 || N > 256 || N % 16 || K < 16 || K > 256 || K % 16 || (mode == 1 && K > 128))
-    return fail(UFO_EINVAL, "ufo_debug_umma_selftest: need 16<=N<=256, 16<=K<=256 (<=128 in mode 1), multiples of 16");
+  if (N < 16 || N > 256 || N % 16 || K < 16 || K > 256 || K % 16 || (mode == 1 && K > 128) || mode < 0 || mode > 2 ||
+      (mode == 2 && (N > 160 || K > 176)))
+    return fail(UFO_EINVAL, "ufo_debug_umma_selftest: need 16<=N<=256, 16<=K<=256 (<=128 in mode 1; N<=160, K<=176 in mode 2), multiples of 16");
   if (int e = check_device()) return e;
   cudaStream_t st = (cudaStream_t)stream_;
   const size_t smem = (size_t)128 * 256 * 2 + (size_t)256 * 256 * 2;
+  if (mode == 2) {   // TS form, two independent halves: A [2][128][K], D [2][128][N]
+    if (bf16) {
+      UFO_CUDA(cudaFuncSetAttribute(k_umma_selftest_ts<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      UFO_KERNEL("k_umma_selftest_ts<true>", st, k_umma_selftest_ts<true><<<1, 256, smem, st>>>(A, B, D, N, K));
+    } else {
+      UFO_CUDA(cudaFuncSetAttribute(k_umma_selftest_ts<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      UFO_KERNEL("k_umma_selftest_ts<false>", st, k_umma_selftest_ts<false><<<1, 256, smem, st>>>(A, B, D, N, K));
+    }
+    return UFO_OK;
+  }
   if (bf16) {
     UFO_CUDA(cudaFuncSetAttribute(k_umma_selftest<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     UFO_KERNEL("k_umma_selftest<true>", st, k_umma_selftest<true><<<1, 128, smem, st>>>(A, B, D, N, K, mode));

@@ -92,4 +92,72 @@ __global__ void __launch_bounds__(128) k_umma_selftest(const float* __restrict__
   if (warp == 0) umma::tmem_dealloc(tmem_base, 256);
 }
 
+
+// mode 2: TS form with TWO independent halves in one CTA (the schedule of the two-tiles-in-flight kernels): half h
+// (threads 128h..128h+127) computes D_h[128][N] = A_h[128][K] . B[N][K]^T with A_h written to TMEM by its row-owner
+// threads (tcgen05.st, packed 16-bit pairs: column j of the operand = K elements 2j, 2j+1), B shared by both halves in
+// shared memory, its own accumulator columns, its own mbarrier, its own issuing thread and a named barrier.
+template <bool kBF16>
+__global__ void __launch_bounds__(256) k_umma_selftest_ts(const float* __restrict__ A, const float* __restrict__ B,
+                                                         float* __restrict__ D, int N, int K) {
+  extern __shared__ __align__(1024) uint8_t smem_u8[];
+  uint8_t* sB = smem_u8;                               // up to 256 x 256 halves
+  __shared__ uint64_t bar[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, h = tid >> 7, r = tid & 127;
+  if (warp == 0) umma::tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) {
+    umma::mbar_init(&bar[0], 1);
+    umma::mbar_init(&bar[1], 1);
+    umma::fence_barrier_init();
+  }
+  for (int c = 0; c < K / 8; ++c)
+    for (int n = tid; n < N; n += 256) {
+      const float* b = B + (size_t)n * K + c * 8;
+      uint4 w;
+      w.x = umma::pack2<kBF16>(b[0], b[1]); w.y = umma::pack2<kBF16>(b[2], b[3]);
+      w.z = umma::pack2<kBF16>(b[4], b[5]); w.w = umma::pack2<kBF16>(b[6], b[7]);
+      *reinterpret_cast<uint4*>(sB + umma::tile_off(N, n, c)) = w;
+    }
+  umma::fence_async_smem();
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tmem = tmem_base_s + 256u * h;                    // this half's 256 columns
+  const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  const uint32_t a_col = 0, d_col = 96;                              // A: K/2 <= 88 columns, D: N <= 160 columns
+  {
+    const float* a = A + ((size_t)h * 128 + r) * K;
+    for (int c = 0; c < K / 8; ++c)
+      umma::tmem_st4(tlane + a_col + 4 * c, umma::pack2<kBF16>(a[8 * c], a[8 * c + 1]), umma::pack2<kBF16>(a[8 * c + 2], a[8 * c + 3]),
+                     umma::pack2<kBF16>(a[8 * c + 4], a[8 * c + 5]), umma::pack2<kBF16>(a[8 * c + 6], a[8 * c + 7]));
+    umma::tmem_st_wait();
+  }
+  umma::tc_fence_before();
+  umma::bar_sync(1 + h, 128);
+  if (r == 0) {
+    umma::tc_fence_after();
+    const uint32_t idesc = umma::make_idesc(128, N, kBF16 ? umma::kFmtBF16 : umma::kFmtF16, false, false);
+    const uint32_t b_lbo = (uint32_t)N * 16u;
+    for (int ks = 0; ks < K / 16; ++ks) {
+      const uint64_t bd = umma::make_smem_desc(umma::smem_u32(sB) + 2 * ks * b_lbo, b_lbo, 128u);
+      umma::mma_f16_ts(tmem + d_col, tmem + a_col + 8 * ks, bd, idesc, ks > 0);
+    }
+    umma::commit(&bar[h]);
+  }
+  umma::mbar_wait(&bar[h], 0);
+  umma::tc_fence_after();
+  for (int n0 = 0; n0 < N; n0 += 16) {
+    float v[16];
+    umma::tmem_ld16(tlane + d_col + n0, v);
+    umma::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (n0 + i < N) D[((size_t)h * 128 + r) * N + n0 + i] = v[i];
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem_base_s, 512);
+}
+
 }  // namespace ufo
