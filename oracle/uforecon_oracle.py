@@ -219,7 +219,7 @@ def ray_transformer(tok: Dict[str, torch.Tensor], sd: Dict[str, torch.Tensor], R
     x = loftr_layer(torch.cat([vt, x], 1), sd, RT + "density_view_transformer.layers.0.")
     a = x[:, 0].reshape(RN, SN, d)
     view_feat = x[:, 1:].reshape(RN, SN, NV, d)
-    pe = order_posenc(8, SN).to(a.dtype)                                           # :302 (.type_as)
+    pe = order_posenc(8, SN).to(a)                                                 # :302 (.type_as)
     r = loftr_layer(torch.cat([a, pe[None].expand(RN, SN, 8)], -1), sd, RT + "density_ray_transformer.layers.0.")
     srdf = _mlp3(r, sd, RT + "DensityMLP.")[..., 0]                                # :307
     om = _mlp3(torch.cat([view_feat, tok["dir"]], -1), sd, RT + "linear_radianceweight_1_softmax.")[..., 0]
@@ -244,7 +244,7 @@ def render(z: torch.Tensor, radiance: torch.Tensor, srdf: torch.Tensor, variance
     prv = srdf - iter_cos * interval * 0.5
     prev_cdf, next_cdf = torch.sigmoid(prv * inv_s), torch.sigmoid(nxt * inv_s)
     alpha = ((prev_cdf - next_cdf + 1e-5) / (prev_cdf + 1e-5)).clip(0.0, 1.0)
-    T = torch.cumprod(torch.cat([torch.ones(RN, 1), 1. - alpha + 1e-7], -1), -1)[:, :-1]
+    T = torch.cumprod(torch.cat([torch.ones(RN, 1).to(alpha), 1. - alpha + 1e-7], -1), -1)[:, :-1]
     w = alpha * T
     return (radiance * w[:, :, None]).sum(1), (w * z).sum(1), w.sum(1), w
 
