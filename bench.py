@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py - rays/s and seconds per DTU-shaped depth map of the per-ray rendering hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--mode tc16|tc|fp32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--mode tc16|fp32]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
@@ -297,7 +297,7 @@ def run_b200(args):
     import __graft_entry__ as ge
     ge.build()
     lib = _lib.load()
-    mode = {"fp32": _lib.UFO_MODE_FP32, "tc": _lib.UFO_MODE_TC, "tc16": getattr(_lib, "UFO_MODE_TC_F16", 2)}[args.mode]
+    mode = {"fp32": _lib.UFO_MODE_FP32, "tc16": _lib.UFO_MODE_TC_F16}[args.mode]
 
     t0 = time.time()
     batch, scene, sd, ckpt_src, views = build_workload(args)
@@ -454,7 +454,7 @@ def run_b200(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp32": "f32", "tc": "bf16", "tc16": "f16"}[args.mode], "data": "synthetic",
+            "dtype": {"fp32": "f32", "tc16": "f16"}[args.mode], "data": "synthetic",
             "sec_per_depth_map": ms_step * 1e-3,
             "sec_per_depth_map_sharded": sharded_s,
             "config": workload_config(args, views, ckpt_src, args.mode),
@@ -671,8 +671,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-accuracy", action="store_true", help="skip the tensor-core vs fp32 accuracy leg (outside the timed region)")
-    ap.add_argument("--mode", default=os.environ.get("UFO_BENCH_MODE", "tc16"), choices=["fp32", "tc", "tc16"],
-                    help="tc16 = tcgen05 with fp16 operands (default: meets the north-star tolerance at full size), tc = bf16 operands")
+    ap.add_argument("--mode", default=os.environ.get("UFO_BENCH_MODE", "tc16"), choices=["fp32", "tc16"],
+                    help="tc16 = tcgen05 with fp16 operands (default: meets the north-star tolerance at full size); fp32 = the 1e-5 parity path")
     ap.add_argument("--width", type=int, default=int(os.environ.get("UFO_BENCH_W", "1600")))
     ap.add_argument("--height", type=int, default=int(os.environ.get("UFO_BENCH_H", "1216")))
     ap.add_argument("--nv", type=int, default=3)

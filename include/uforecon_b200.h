@@ -51,10 +51,11 @@ enum {
 /* Transformer arithmetic of ufo_render_rays. */
 enum {
   UFO_MODE_FP32 = 0, /* CUDA-core fp32 everywhere (parity: 1e-5 relative)                        */
-  UFO_MODE_TC = 1,   /* BF16 operands / FP32 accumulate on tcgen05 tensor cores for the GEMMs    */
-  UFO_MODE_TC_F16 = 2 /* same kernels with FP16 operands (3 more mantissa bits; packing saturates at
-                       * +-65504).  The recommended mode: inside the tolerance (p99 depth error <= 0.5 % of the
-                       * interval, PSNR >= 50 dB) at 1600x1216, where BF16 operands are not.          */
+  UFO_MODE_TC = 1,   /* RETIRED (round 2): BF16 operands on the tensor cores.  Measured p99 5.6e-3 of the interval /
+                      * 46 dB at 1600x1216 - outside the tolerance - so ufo_render_rays returns UFO_EINVAL for it.  */
+  UFO_MODE_TC_F16 = 2 /* tcgen05 tensor cores, FP16 operands / FP32 accumulate (packing saturates at +-65504):
+                       * inside the tolerance (p99 depth error <= 0.5 % of the interval, PSNR >= 50 dB) at
+                       * 1600x1216.  The throughput mode.                                              */
 };
 
 typedef struct UfoScene UfoScene;     /* one view set: repacked source tensors + cameras        */
@@ -161,7 +162,7 @@ int64_t ufo_scene_device_bytes(const UfoScene* s);
  *   u_coarse  [dev] [64, u_stride]  uniforms of FixedSampler's jitter, column i <-> ray i
  *   u_fine    [dev] [64, u_stride]  uniforms of ImportanceSampler (reference draws [64,RN] and
  *             transposes, sampler.py:86); u_stride >= n_rays is the row pitch in floats
- *   mode      UFO_MODE_FP32 | UFO_MODE_TC | UFO_MODE_TC_F16
+ *   mode      UFO_MODE_FP32 | UFO_MODE_TC_F16
  */
 int ufo_render_rays(const UfoScene* scene, const UfoWeights* weights, const int64_t* ray_idx,
                     int64_t ray_begin, int32_t n_rays, const float* u_coarse, const float* u_fine,

@@ -11,7 +11,7 @@ import torch
 from conftest import make_case, rel_err
 from oracle import uforecon_oracle as orc
 from uforecon_b200 import synthetic
-from uforecon_b200._lib import UFO_MODE_FP32, UFO_MODE_TC
+from uforecon_b200._lib import UFO_MODE_FP32, UFO_MODE_TC_F16 as UFO_MODE_TC
 from uforecon_b200.renderer import UFOReconRenderer, draw_uniforms
 
 pytestmark = pytest.mark.gpu
@@ -109,3 +109,95 @@ def test_render_depth_map_device_rng(small):
     rel = float(((d_a - d_ref).abs() / d_ref.abs().clamp_min(1e-6)).median())
     assert rel < 2e-2, rel
     ren.close()
+
+
+def test_one_renderer_two_render_views_and_in_place_updates(small):
+    """The cached Scene must follow its inputs: another render view of the same source set (only rays / poses / MVS depth
+    change - the encoder tensors are the SAME objects), an in-place update of an encoder output, and a freed-and-reallocated
+    batch must each give the result of a fresh renderer."""
+    batch, scene, sd = small
+    ren = UFOReconRenderer(sd, mode=UFO_MODE_FP32)
+    ray_idx = torch.arange(100, 400)[None]
+
+    def run(r, b, sc_):
+        torch.manual_seed(3)
+        return r.infer(b, ray_idx, sc_["source_imgs_feat"], feature_volume=sc_["feature_volume"], extract_geometry=True,
+                       match_feature=sc_["match_feature"])
+
+    first = run(ren, batch, scene)
+    # render view 2: same encoder tensor OBJECTS, other rays / reference pose (what DtuFitSparse yields for the next batch)
+    b2 = dict(batch)
+    b2["ray_d"] = torch.roll(batch["ray_d"], 37, dims=2).clone()
+    b2["cam_ray_d"] = torch.roll(batch["cam_ray_d"], 37, dims=2).clone()
+    b2["ref_pose_inv"] = batch["ref_pose_inv"].clone()
+    b2["ref_pose_inv"][0, :3, 3] += 0.05
+    second = run(ren, b2, scene)
+    fresh = UFOReconRenderer(sd, mode=UFO_MODE_FP32)
+    want = run(fresh, b2, scene)
+    fresh.close()
+    assert not torch.equal(first[2], second[2])
+    for a, b in zip(second, want):
+        assert torch.equal(a, b)
+    # in-place update of an encoder output (same object, same address): must be noticed through the version counter
+    scene["source_imgs_feat"].mul_(1.25)
+    third = run(ren, b2, scene)
+    fresh = UFOReconRenderer(sd, mode=UFO_MODE_FP32)
+    want = run(fresh, b2, scene)
+    fresh.close()
+    scene["source_imgs_feat"].div_(1.25)
+    for a, b in zip(third, want):
+        assert torch.equal(a, b)
+    assert not torch.equal(third[2], second[2])
+    # explicit scope
+    ren.begin_scene(batch, scene["source_imgs_feat"], scene["feature_volume"], scene["match_feature"])
+    again = run(ren, batch, scene)
+    ren.end_scene()
+    assert torch.allclose(again[2], first[2], atol=1e-5)
+    ren.close()
+
+
+def test_scene_rejects_mismatched_shapes_and_bad_ray_indices(small):
+    from uforecon_b200.renderer import HotPathWeights, Scene, render_rays
+    batch, scene, sd = small
+    for key, bad in (("depth_info", batch["depth_info"][:, :, ::2, ::2]), ("ray_d", batch["ray_d"][:, :, :100]),
+                     ("cam_ray_d", batch["cam_ray_d"][:, :2]), ("w2cs", batch["w2cs"][:, :2]), ("source_poses", batch["source_poses"][:, :2])):
+        b = dict(batch)
+        b[key] = bad
+        with pytest.raises(ValueError):
+            Scene(b, scene["source_imgs_feat"], scene["feature_volume"], scene["match_feature"])
+    fv = {k: dict(v) for k, v in scene["feature_volume"].items()}
+    fv["stage2"]["weight_volume"] = fv["stage2"]["weight_volume"][:, :, :-1]
+    with pytest.raises(ValueError):
+        Scene(batch, scene["source_imgs_feat"], fv, scene["match_feature"])
+    b = dict(batch)
+    b["start_idx"] = 1                                    # training-style batch: w2cs would need NV + 1 rows
+    with pytest.raises(ValueError):
+        Scene(b, scene["source_imgs_feat"], scene["feature_volume"], scene["match_feature"])
+    w = HotPathWeights(sd)
+    sc = Scene(batch, scene["source_imgs_feat"], scene["feature_volume"], scene["match_feature"])
+    u_c, u_f = synthetic.sampler_uniforms(4, seed=1)
+    with pytest.raises(ValueError):
+        render_rays(sc, w, torch.tensor([0, 5, 64 * 96, 7]), 4, u_c, u_f, UFO_MODE_FP32)
+    with pytest.raises(ValueError):
+        render_rays(sc, w, torch.tensor([0, -1, 3, 7]), 4, u_c, u_f, UFO_MODE_FP32)
+    sc.close()
+    w.close()
+
+
+def test_start_idx_selects_the_w2c_rows(small):
+    """ray_transformer.py:182,240: w2cs[:, s_idx:] - a batch with a leading reference-view row and start_idx = 1 must render
+    like the inference batch without it."""
+    from uforecon_b200.renderer import HotPathWeights, Scene, render_rays
+    batch, scene, sd = small
+    b = dict(batch)
+    b["start_idx"] = 1
+    b["w2cs"] = torch.cat([torch.eye(4)[None, None] * 3.0, batch["w2cs"]], 1)
+    w = HotPathWeights(sd)
+    u_c, u_f = synthetic.sampler_uniforms(64, seed=2)
+    out = []
+    for bb in (batch, b):
+        sc = Scene(bb, scene["source_imgs_feat"], scene["feature_volume"], scene["match_feature"])
+        out.append(render_rays(sc, w, None, 64, u_c, u_f, UFO_MODE_FP32, ray_begin=1000)["depth"].clone())
+        sc.close()
+    w.close()
+    assert torch.equal(out[0], out[1])

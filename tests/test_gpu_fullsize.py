@@ -11,16 +11,30 @@ import torch
 from conftest import make_case, rel_err
 from oracle import uforecon_oracle as orc
 from uforecon_b200 import synthetic
-from uforecon_b200._lib import UFO_MODE_FP32, UFO_MODE_TC, UFO_MODE_TC_F16
+from uforecon_b200._lib import UFO_MODE_FP32, UFO_MODE_TC_F16
 
 pytestmark = pytest.mark.gpu
 
 W, H = 1600, 1216
-# north star: p99 depth error <= 0.5 % of the depth interval, colour PSNR >= 50 dB.  fp16 operands (the default mode) are
-# held to it; bf16 operands (8 mantissa bits) measure 5.6e-3 / 46 dB on this scene - outside the bound, which is why bf16
-# is not the default - and are only held to "no worse than measured" so that a regression still shows
-P99_BOUND = {UFO_MODE_TC_F16: 5e-3, UFO_MODE_TC: 8e-3}
-PSNR_BOUND = {UFO_MODE_TC_F16: 50.0, UFO_MODE_TC: 44.0}
+# north star: p99 depth error <= 0.5 % of the depth interval, colour PSNR >= 50 dB, for the tensor-core mode (fp16 operands).
+# bf16 operands measured 5.6e-3 / 46 dB on this scene in round 1 - outside the bound - and were retired (ufo_render_rays
+# rejects UFO_MODE_TC), so there is no second bound here.
+P99_BOUND = 5e-3
+PSNR_BOUND = 50.0
+# strict reading of "depth interval" (SURVEY.md D3): cam.txt DEPTH_INTERVAL = 2.5 mm; reported next to the lenient one
+DEPTH_INTERVAL_MM = 2.5
+
+
+def to64(o, device=None):
+    """float tensors of a nested batch / scene / state dict as float64 (optionally on `device`): the fp64 referee"""
+    if torch.is_tensor(o):
+        o = o.double() if o.is_floating_point() else o
+        return o.to(device) if device is not None else o
+    if isinstance(o, dict):
+        return {k: to64(v, device) for k, v in o.items()}
+    if isinstance(o, (list, tuple)):
+        return type(o)(to64(v, device) for v in o)
+    return o
 
 
 @pytest.fixture(scope="module")
@@ -54,11 +68,12 @@ def test_fullsize_fp32_sample_vs_oracle(full):
     with torch.no_grad():
         k = orc.sample2rgb(batch, scene, sd, pts, r["z"], detail=True)          # oracle at the CUDA path's own samples
         o = orc.infer(batch, scene, sd, ray_idx, u_c, u_f, detail=True)         # oracle end to end
-        # conditioning of the path at this resolution: the oracle itself with every point coordinate moved by one
-        # fp32 ulp.  One ulp of u is 1e-7 * 800 pixels here (5x the small cases) and the synthetic fields change by
-        # O(0.1) per pixel, so the kernels cannot agree with ANY other evaluation order to better than this
-        sgn = torch.randint(0, 2, pts.shape, generator=g).float() * 2 - 1
-        k2 = orc.sample2rgb(batch, scene, sd, pts * (1 + 1.2e-7 * sgn), r["z"], detail=True)
+        # fp64 referee: the same restatement evaluated in float64 (on the GPU: the 4.3 GB scene as doubles) at the SAME fp32
+        # sample positions.  It says how far the fp32 oracle (= the reference's own arithmetic) is from the true value
+        # of its formulas at this resolution - one ulp of u is 1e-7 * 800 pixels here - and the kernel must be as close
+        # to that true value as the reference is: |kernel - fp64| <= 2 |oracle_fp32 - fp64| + 1e-5 per tensor.
+        k64 = orc.sample2rgb(to64(batch, "cuda"), to64(scene, "cuda"), to64(sd, "cuda"), pts.double().cuda(), r["z"].double().cuda(), detail=True)
+        k64 = {a: (v.cpu() if torch.is_tensor(v) else v) for a, v in k64.items()}
 
     def split(t):
         t = t.view(n, 128, 3, 80)
@@ -72,14 +87,16 @@ def test_fullsize_fp32_sample_vs_oracle(full):
         return {"sim8": d["sim8"], "vol24": d["vol24"], **split(d["tokens"]), "view_tok0": d["view_out"].view(n, 128, 4, 80)[:, :, 0],
                 "ray_out": d["ray_out"], "srdf": d["srdf"], "radiance": d["radiance"][~amb]}
 
-    ka, kb = ref_of(k), ref_of(k2)
-    err = {a: rel_err(ours[a], ka[a]) for a in ours}
-    cond = {a: rel_err(kb[a], ka[a]) for a in ours}
+    ka, k8 = ref_of(k), ref_of(k64)
+    err = {a: rel_err(ours[a], ka[a]) for a in ours}            # kernel vs fp32 oracle
+    err64 = {a: rel_err(ours[a], k8[a]) for a in ours}          # kernel vs fp64 referee
+    orc64 = {a: rel_err(ka[a], k8[a]) for a in ours}            # fp32 oracle vs fp64 referee
     base = {a: (1e-5 if a in ("sim8", "vol24", "feat", "vol_tok", "sim16") else 1e-4) for a in ours}      # test_gpu_parity.py bars
-    print("fullsize fp32 isolated err :", {a: f"{b:.1e}" for a, b in err.items()})
-    print("fullsize 1-ulp conditioning:", {a: f"{b:.1e}" for a, b in cond.items()})
+    print("fullsize fp32 kernel vs fp32 oracle :", {a: f"{b:.1e}" for a, b in err.items()})
+    print("fullsize fp32 kernel vs fp64 referee:", {a: f"{b:.1e}" for a, b in err64.items()})
+    print("fullsize fp32 oracle vs fp64 referee:", {a: f"{b:.1e}" for a, b in orc64.items()})
     for a in ours:
-        assert err[a] <= base[a] + 3 * cond[a], (a, err[a], cond[a])
+        assert err64[a] <= 2 * orc64[a] + base[a], (a, err64[a], orc64[a])
     with torch.no_grad():
         rgb, depth, _, weight = orc.render(r["z"], r["radiance"], r["srdf"], sd["deviation_network.variance"])
     comp = {"weight": rel_err(r["weight"], weight), "depth": rel_err(r["depth"], depth), "rgb": rel_err(r["rgb"], rgb)}
@@ -89,13 +106,22 @@ def test_fullsize_fp32_sample_vs_oracle(full):
     print("fullsize fp32 isolated compositing:", {a: f"{b:.1e}" for a, b in comp.items()})
     print("fullsize fp32 end to end:", {a: f"{b:.1e}" for a, b in e2e.items()}, "ambiguous rays", int((~clean).sum()))
     assert all(v <= 1e-5 for v in comp.values()), comp
+    # tensor-core mode DIRECTLY against the oracle on the same rays and uniforms (not through the fp32 mode)
+    t = render_rays(full["sc"], full["w"], ray_idx, n, u_c, u_f, UFO_MODE_TC_F16, want=("depth", "rgb"))
+    torch.cuda.synchronize()
+    span = float(batch["near_fars"][0, 0, 1] - batch["near_fars"][0, 0, 0])
+    de = (t["depth"].cpu() - o["depth"]).abs() / span
+    mse = float(((t["rgb"].cpu() - o["rgb"])[~amb.any(1)] ** 2).mean())
+    print(f"fullsize tc16 vs oracle on {n} rays: depth err/interval p99 {float(de.quantile(0.99)):.2e} max {float(de.max()):.2e}, "
+          f"colour PSNR {10 * math.log10(1.0 / max(mse, 1e-20)):.1f} dB")
+    assert float(de.quantile(0.99)) <= P99_BOUND and 10 * math.log10(1.0 / max(mse, 1e-20)) >= PSNR_BOUND
     # end to end the inverse-CDF sampler divides by the coarse weight of the hit bin, so a fine sample in a bin of
     # near-zero weight moves by far more than the rounding upstream (bound in test_importance_sampler_isolated); the
     # rendered depth is insensitive to it, the colour of a ray whose moved sample carries weight is not
     assert e2e["depth"] <= 1e-4 and e2e["depth_z"] <= 1e-4 and e2e["z"] <= 1e-3 and e2e["rgb"] <= 1e-3, e2e
 
 
-@pytest.mark.parametrize("mode", [UFO_MODE_TC_F16, UFO_MODE_TC])
+@pytest.mark.parametrize("mode", [UFO_MODE_TC_F16])
 def test_fullsize_map_properties(full, mode):
     """Full 1.9 M-ray map in tensor-core mode: finite, inside the sampled range, bit-identical when row bands are
     rendered on their own, and within the north-star tolerance of the fp32 path on those bands."""
@@ -141,5 +167,10 @@ def test_fullsize_map_properties(full, mode):
     de = torch.cat(de_all)
     p99, psnr = float(de.quantile(0.99)), 10 * math.log10(1.0 / max(se / cnt, 1e-20))
     print(f"fullsize mode {mode}: depth err/interval p99 {p99:.2e}, colour PSNR {psnr:.1f} dB over {len(de)} rays")
-    assert p99 <= P99_BOUND[mode], p99
-    assert psnr >= PSNR_BOUND[mode], psnr
+    # strict reading of the tolerance ("report both"): the error in mm against 0.5 % of cam.txt's 2.5 mm
+    # DEPTH_INTERVAL = 0.0125 mm - below fp16 operand rounding by construction; printed, not asserted
+    mm = p99 * span * float(batch["scale_mat"][0, 0, 0]) if "scale_mat" in batch else float("nan")
+    print(f"fullsize mode {mode}: strict reading: p99 depth error {mm:.3f} mm = {mm / DEPTH_INTERVAL_MM:.3f} of the 2.5 mm DEPTH_INTERVAL "
+          f"(north-star bound read strictly: 0.005)")
+    assert p99 <= P99_BOUND, p99
+    assert psnr >= PSNR_BOUND, psnr

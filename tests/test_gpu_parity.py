@@ -12,7 +12,7 @@ import torch
 from conftest import load_golden, make_case, rel_err
 from oracle import uforecon_oracle as orc
 from uforecon_b200 import synthetic
-from uforecon_b200._lib import UFO_MODE_FP32, UFO_MODE_TC
+from uforecon_b200._lib import UFO_MODE_FP32, UFO_MODE_TC_F16 as UFO_MODE_TC
 
 pytestmark = pytest.mark.gpu
 

@@ -4,7 +4,8 @@ Tolerances (BASELINE.json north_star): against the reference arithmetic on ident
 transformer path must keep the p99 per-pixel depth error <= 0.5 % of the depth interval (the ray's sampled range
 far - near) and the rendered-colour PSNR >= 50 dB.  The isolated checks feed the oracle the CUDA
 path's own sample positions, so each bound is a statement about the 16-bit-operand kernels alone:
-bf16 operands carry 8 mantissa bits (2^-9 relative rounding), fp16 11 bits (2^-12).
+fp16 operands carry 11 mantissa bits (2^-12 relative rounding).  The bf16-operand mode (8 bits) of round 1 missed the
+tolerance at the BASELINE size and was retired: the library rejects UFO_MODE_TC.
 """
 import math
 import os
@@ -15,14 +16,14 @@ import torch
 from conftest import make_case, rel_err
 from oracle import uforecon_oracle as orc
 from uforecon_b200 import synthetic
-from uforecon_b200._lib import UFO_MODE_FP32, UFO_MODE_TC, UFO_MODE_TC_F16
+from uforecon_b200._lib import UFO_MODE_FP32, UFO_MODE_TC, UFO_MODE_TC_F16, UfoError
 
 pytestmark = pytest.mark.gpu
 
 TAPS = ("z_coarse", "weight_coarse", "srdf_coarse", "z_fine", "sim8", "vol24", "tokens", "view_tok0", "ray_out", "radiance",
         "weight")
 # per mode: (token rounding, view stage, ray stage, srdf) relative bounds = max|a-b| / max|ref|
-BOUNDS = {UFO_MODE_TC: (6e-3, 1.2e-2, 1.5e-2, 3e-2), UFO_MODE_TC_F16: (8e-4, 2e-3, 2e-3, 3e-3)}
+BOUNDS = {UFO_MODE_TC_F16: (8e-4, 2e-3, 2e-3, 3e-3)}
 
 
 @pytest.fixture(scope="module", params=[3, 5, 2, 10])
@@ -38,7 +39,7 @@ def tc_case(request):
     w = HotPathWeights(sd)
     sc = Scene(batch, scene["source_imgs_feat"], scene["feature_volume"], scene["match_feature"])
     out = {}
-    for mode in (UFO_MODE_FP32, UFO_MODE_TC, UFO_MODE_TC_F16):
+    for mode in (UFO_MODE_FP32, UFO_MODE_TC_F16):
         r = render_rays(sc, w, ray_idx, n, u_c, u_f, mode, want=("depth", "depth_z", "rgb", "srdf", "z", "points"), taps=TAPS)
         torch.cuda.synchronize()
         out[mode] = {k: v.cpu() for k, v in r.items()}
@@ -47,7 +48,7 @@ def tc_case(request):
     return dict(batch=batch, scene=scene, sd=sd, ray_idx=ray_idx, n=n, nv=nv, out=out)
 
 
-@pytest.mark.parametrize("mode", [UFO_MODE_TC, UFO_MODE_TC_F16])
+@pytest.mark.parametrize("mode", [UFO_MODE_TC_F16])
 def test_tc_kernels_isolated(tc_case, mode):
     """gather (16-bit tokens) -> view stage -> ray stage -> SRDF head at the CUDA path's own sample positions."""
     c = tc_case
@@ -75,12 +76,19 @@ def test_tc_kernels_isolated(tc_case, mode):
     assert rel_err(r["depth"], depth) <= 1e-5 and rel_err(r["rgb"], rgb) <= 1e-5 and rel_err(r["weight"], weight) <= 1e-5
 
 
-@pytest.mark.parametrize("mode", [UFO_MODE_TC, UFO_MODE_TC_F16])
+@pytest.mark.parametrize("mode", [UFO_MODE_TC_F16])
 def test_tc_end_to_end_tolerance(tc_case, mode):
-    """north-star tolerance against the fp32 path (itself 1e-4 from the reference, test_gpu_parity.py)."""
+    """north-star tolerance DIRECTLY against the oracle (the reference's arithmetic) on the same rays and uniforms, and
+    against the fp32 mode of the library."""
     c = tc_case
     r, ref = c["out"][mode], c["out"][UFO_MODE_FP32]
     batch = c["batch"]
+    u_c, u_f = synthetic.sampler_uniforms(c["n"], seed=7)
+    with torch.no_grad():
+        o = orc.infer(batch, c["scene"], c["sd"], c["ray_idx"], u_c, u_f)
+    span0 = float(batch["near_fars"][0, 0, 1] - batch["near_fars"][0, 0, 0])
+    de_o = (r["depth"] - o["depth"]).abs() / span0
+    assert float(de_o.quantile(0.99)) <= 5e-3, float(de_o.quantile(0.99))
     span = float(batch["near_fars"][0, 0, 1] - batch["near_fars"][0, 0, 0])
     de = (r["depth"] - ref["depth"]).abs() / span
     assert float(de.quantile(0.99)) <= 5e-3, float(de.quantile(0.99))
@@ -96,6 +104,8 @@ def test_tc_end_to_end_tolerance(tc_case, mode):
     assert float(amb.float().mean()) < 0.15
     mse = float(((r["rgb"] - ref["rgb"])[~amb] ** 2).mean())
     assert 10 * math.log10(1.0 / max(mse, 1e-20)) >= 50.0
+    mse_o = float(((r["rgb"] - o["rgb"])[~amb] ** 2).mean())
+    assert 10 * math.log10(1.0 / max(mse_o, 1e-20)) >= 50.0, 10 * math.log10(1.0 / max(mse_o, 1e-20))
 
 
 def test_tc_chunking_invariance():
@@ -106,16 +116,57 @@ def test_tc_chunking_invariance():
     u_c, u_f = synthetic.sampler_uniforms(n, seed=5)
     w = HotPathWeights(sd)
     sc = Scene(batch, scene["source_imgs_feat"], scene["feature_volume"], scene["match_feature"])
-    full = render_rays(sc, w, None, n, u_c, u_f, UFO_MODE_TC, ray_begin=700)
+    full = render_rays(sc, w, None, n, u_c, u_f, UFO_MODE_TC_F16, ray_begin=700)
     os.environ["UFO_TC_CHUNK"] = "77"
     try:
-        tiled = render_rays(sc, w, None, n, u_c, u_f, UFO_MODE_TC, ray_begin=700)
+        tiled = render_rays(sc, w, None, n, u_c, u_f, UFO_MODE_TC_F16, ray_begin=700)
     finally:
         del os.environ["UFO_TC_CHUNK"]
-    part = render_rays(sc, w, None, 100, u_c[:, 100:200].contiguous(), u_f[:, 100:200].contiguous(), UFO_MODE_TC, ray_begin=800)
+    part = render_rays(sc, w, None, 100, u_c[:, 100:200].contiguous(), u_f[:, 100:200].contiguous(), UFO_MODE_TC_F16, ray_begin=800)
     torch.cuda.synchronize()
     for k in ("depth", "rgb", "depth_z"):
         assert torch.equal(full[k], tiled[k]), k
         assert torch.equal(full[k][100:200], part[k]), k
     sc.close()
     w.close()
+
+
+def test_bf16_mode_is_retired():
+    """UFO_MODE_TC (bf16 operands) measured p99 5.6e-3 / 46 dB at 1600x1216 in round 1 - outside the north-star tolerance:
+    the library refuses it instead of rendering out of tolerance."""
+    from uforecon_b200.renderer import HotPathWeights, Scene, render_rays
+    batch, scene, sd = make_case(synthetic.UNFAVORABLE_VIEWS, (96, 64))
+    u_c, u_f = synthetic.sampler_uniforms(8, seed=5)
+    w = HotPathWeights(sd)
+    sc = Scene(batch, scene["source_imgs_feat"], scene["feature_volume"], scene["match_feature"])
+    with pytest.raises(UfoError):
+        render_rays(sc, w, None, 8, u_c, u_f, UFO_MODE_TC, ray_begin=0)
+    sc.close()
+    w.close()
+
+
+@pytest.mark.parametrize("name", ["infer_nv3.npz", "infer_nv5.npz"])
+def test_tc_against_reference_goldens(name):
+    """tensor-core mode against the outputs of the UNMODIFIED reference committed under tests/golden (tools/make_golden.py):
+    the north-star tolerance measured against the reference itself, no oracle and no fp32 mode in between."""
+    from conftest import load_golden
+    from uforecon_b200.renderer import HotPathWeights, Scene, render_rays
+    g = load_golden(name)
+    Wd, Hd, seed, _ = [int(x) for x in g["meta"][:4]]
+    views = [int(x) for x in g["meta"][4:]]
+    batch, scene, sd = make_case(views, (Wd, Hd))
+    ray_idx = torch.from_numpy(g["ray_idx"]).long()
+    n = len(ray_idx)
+    u_c, u_f = synthetic.sampler_uniforms(n, seed=seed)
+    w = HotPathWeights(sd)
+    sc = Scene(batch, scene["source_imgs_feat"], scene["feature_volume"], scene["match_feature"])
+    r = render_rays(sc, w, ray_idx, n, u_c, u_f, UFO_MODE_TC_F16, want=("depth", "rgb"))
+    torch.cuda.synchronize()
+    sc.close()
+    w.close()
+    span = float(batch["near_fars"][0, 0, 1] - batch["near_fars"][0, 0, 0])
+    de = (r["depth"].cpu() - torch.from_numpy(g["depth"])).abs() / span
+    mse = float(((r["rgb"].cpu() - torch.from_numpy(g["rgb"])) ** 2).mean())
+    print(f"{name}: tc16 vs reference golden: depth err/interval p99 {float(de.quantile(0.99)):.2e}, colour PSNR {10 * math.log10(1 / max(mse, 1e-20)):.1f} dB")
+    assert float(de.quantile(0.99)) <= 5e-3
+    assert 10 * math.log10(1.0 / max(mse, 1e-20)) >= 45.0     # includes mask-ambiguous rays (see test_tc_end_to_end_tolerance)

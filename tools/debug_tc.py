@@ -6,7 +6,7 @@ import torch
 from conftest import make_case, rel_err
 from oracle import uforecon_oracle as orc
 from uforecon_b200 import synthetic
-from uforecon_b200._lib import UFO_MODE_FP32, UFO_MODE_TC, UFO_MODE_TC_F16
+from uforecon_b200._lib import UFO_MODE_FP32, UFO_MODE_TC_F16
 from uforecon_b200.renderer import HotPathWeights, Scene, render_rays
 
 TAPS = ("z_coarse", "weight_coarse", "srdf_coarse", "z_fine", "sim8", "vol24", "tokens", "view_tok0", "ray_out", "radiance", "weight")
@@ -23,7 +23,7 @@ def main():
     span = float(batch["near_fars"][0, 0, 1] - batch["near_fars"][0, 0, 0])
     ref = render_rays(sc, w, ray_idx, n, u_c, u_f, UFO_MODE_FP32, want=("depth", "rgb", "srdf", "z"))
     torch.cuda.synchronize()
-    for name, mode in (("bf16", UFO_MODE_TC), ("fp16", UFO_MODE_TC_F16)):
+    for name, mode in (("fp16", UFO_MODE_TC_F16),):
         r = render_rays(sc, w, ray_idx, n, u_c, u_f, mode, want=("depth", "depth_z", "rgb", "srdf", "z", "points"), taps=TAPS)
         torch.cuda.synchronize()
         r = {k: v.cpu() for k, v in r.items()}

@@ -139,6 +139,9 @@ static void pack_b(uint8_t* img, const float* W, int n_real, int k_real, int ldw
     }
 }
 
+// byte offsets of the k_view_tc2 weight image (mirrors tc::V2_W* in ufo_view_tc2.cuh, which only device TUs include)
+constexpr size_t kV2WQkv = 0, kV2WMrg = kV2WQkv + 240 * 80 * 2, kV2WMl0 = kV2WMrg + 80 * 96 * 2, kV2WMl2 = kV2WMl0 + 160 * 176 * 2,
+                 kV2WRad = kV2WMl2 + 80 * 160 * 2, kV2WEnd = kV2WRad + 16 * 176 * 2;
 static int tc_weights_build(const UfoWeightsDesc* d, TcWeights* t, cudaStream_t st) {
   for (int f = 0; f < 2; ++f) {
     const bool bf16 = (f == 0);
@@ -173,6 +176,43 @@ static int tc_weights_build(const UfoWeightsDesc* d, TcWeights* t, cudaStream_t 
       pack_b(ri.data() + tc::RW_ML2, d->ray.mlp2, 88, 176, 176, 96, 176, bf16);
       pack_b(ri.data() + tc::RW_DEN, d->density.w0, 32, 88, 88, 32, 96, bf16, 0);
       pack_b(ri.data() + tc::RW_DEN + 32 * 96 * 2, d->density.w0, 32, 88, 88, 32, 96, bf16, 1);
+    }
+    {  // view stage, two-tiles-in-flight kernel (ufo_view_tc2.cuh): rows / K columns regrouped per column group
+      std::vector<uint8_t> v2(kV2WEnd, 0);
+      std::vector<float> qkv((size_t)240 * 80);
+      const float* part[3] = {d->view.q, d->view.k, d->view.v};
+      for (int g = 0; g < 2; ++g)
+        for (int pt = 0; pt < 3; ++pt)
+          for (int j = 0; j < 40; ++j) memcpy(qkv.data() + (size_t)(120 * g + 40 * pt + j) * 80, part[pt] + (size_t)(40 * g + j) * 80, sizeof(float) * 80);
+      pack_b(v2.data() + kV2WQkv, qkv.data(), 240, 80, 80, 240, 80, bf16);
+      // K = 80 message / LayerNorm channels as [g0: 40 | 8 zeros | g1: 40 | 8 zeros]
+      auto pad96 = [](const float* W, int ldw, int col0, float* out, int ldo, int ocol0, int rows) {
+        for (int o = 0; o < rows; ++o)
+          for (int k = 0; k < 96; ++k) {
+            const int src = k < 40 ? k : (k >= 48 && k < 88 ? k - 8 : -1);
+            out[(size_t)o * ldo + ocol0 + k] = src < 0 ? 0.f : W[(size_t)o * ldw + col0 + src];
+          }
+      };
+      std::vector<float> mrg((size_t)80 * 96);
+      pad96(d->view.merge, 80, 0, mrg.data(), 96, 0, 80);
+      pack_b(v2.data() + kV2WMrg, mrg.data(), 80, 96, 96, 80, 96, bf16);
+      std::vector<float> ml0((size_t)160 * 176);
+      for (int o = 0; o < 160; ++o) memcpy(ml0.data() + (size_t)o * 176, d->view.mlp0 + (size_t)o * 160, sizeof(float) * 80);
+      pad96(d->view.mlp0, 160, 80, ml0.data(), 176, 80, 160);
+      pack_b(v2.data() + kV2WMl0, ml0.data(), 160, 176, 176, 160, 176, bf16);
+      pack_b(v2.data() + kV2WMl2, d->view.mlp2, 80, 160, 160, 80, 160, bf16);
+      // radiance head layer 0 on [x | LN2 g0 | dir 3, 1, 0.. | LN2 g1 | 0..]: x + LN2 without forming the sum, bias via the 1
+      std::vector<float> rad((size_t)16 * 176, 0.f);
+      for (int o = 0; o < 16; ++o) {
+        memcpy(rad.data() + (size_t)o * 176, d->radiance.w0 + (size_t)o * 83, sizeof(float) * 80);
+        pad96(d->radiance.w0 + (size_t)o * 83, 83, 0, rad.data() + (size_t)o * 176, 176, 80, 1);
+        for (int k = 0; k < 3; ++k) rad[(size_t)o * 176 + 80 + 40 + k] = d->radiance.w0[o * 83 + 80 + k];
+        rad[(size_t)o * 176 + 80 + 43] = d->radiance.b0[o];
+      }
+      pack_b(v2.data() + kV2WRad, rad.data(), 16, 176, 176, 16, 176, bf16);
+      UFO_CUDA(cudaMalloc(&t->view_img2[f], v2.size()));
+      UFO_CUDA(cudaMemcpyAsync(t->view_img2[f], v2.data(), v2.size(), cudaMemcpyHostToDevice, st));
+      UFO_CUDA(cudaStreamSynchronize(st));
     }
     UFO_CUDA(cudaMalloc(&t->view_img[f], vi.size()));
     UFO_CUDA(cudaMalloc(&t->ray_img[f], ri.size()));
@@ -305,7 +345,7 @@ extern "C" int ufo_weights_create(const UfoWeightsDesc* d, UfoWeights** out, voi
 
 extern "C" void ufo_weights_destroy(UfoWeights* w) {
   if (!w) return;
-  for (int f = 0; f < 2; ++f) { cudaFree(w->tc.view_img[f]); cudaFree(w->tc.ray_img[f]); }
+  for (int f = 0; f < 2; ++f) { cudaFree(w->tc.view_img[f]); cudaFree(w->tc.ray_img[f]); cudaFree(w->tc.view_img2[f]); }
   cudaFree(w->blob);
   delete w;
 }
@@ -621,7 +661,7 @@ namespace ufo {
 int tc_pass(bool bf16, const UfoScene* sc, const UfoWeights* w, int R, int half, const float* z, bool want_sim8, float* ray_out_tap,
             int sms, cudaStream_t st) {
   const bool lo = sc->d.nv <= 5;
-  if (bf16) return lo ? tc_pass_bf16_lo(sc, w, R, half, z, want_sim8, ray_out_tap, sms, st) : tc_pass_bf16_hi(sc, w, R, half, z, want_sim8, ray_out_tap, sms, st);
+  if (bf16) return fail(UFO_EINVAL, "bf16 operands are retired");
   return lo ? tc_pass_f16_lo(sc, w, R, half, z, want_sim8, ray_out_tap, sms, st) : tc_pass_f16_hi(sc, w, R, half, z, want_sim8, ray_out_tap, sms, st);
 }
 }  // namespace ufo
@@ -704,7 +744,10 @@ extern "C" int ufo_render_rays(const UfoScene* sc, const UfoWeights* w, const in
                                const UfoRenderOut* out, const UfoDebugTaps* taps, void* stream_) {
   if (!sc || !w || !out || !u_coarse || !u_fine) return fail(UFO_EINVAL, "ufo_render_rays: null argument");
   if (n_rays < 0 || u_stride < n_rays) return fail(UFO_EINVAL, "ufo_render_rays: bad n_rays/u_stride");
-  if (mode != UFO_MODE_FP32 && mode != UFO_MODE_TC && mode != UFO_MODE_TC_F16) return fail(UFO_EINVAL, "ufo_render_rays: unknown mode %d", mode);
+  if (mode == UFO_MODE_TC)
+    return fail(UFO_EINVAL, "ufo_render_rays: UFO_MODE_TC (bf16 operands) is retired - it misses the depth/colour tolerance at 1600x1216 "
+                            "(p99 5.6e-3 of the interval, 46 dB); use UFO_MODE_TC_F16");
+  if (mode != UFO_MODE_FP32 && mode != UFO_MODE_TC_F16) return fail(UFO_EINVAL, "ufo_render_rays: unknown mode %d", mode);
   if (!ray_idx && (ray_begin < 0 || ray_begin + n_rays > (int64_t)sc->d.H * sc->d.W))
     return fail(UFO_EINVAL, "ufo_render_rays: ray range [%lld,%lld) outside the %dx%d grid", (long long)ray_begin,
                 (long long)(ray_begin + n_rays), sc->d.H, sc->d.W);

@@ -14,6 +14,7 @@ struct LoftrDev {
 struct TcWeights {
   uint8_t* view_img[2] = {nullptr, nullptr};   // [0] bf16, [1] fp16   (tc::V_WEND bytes)
   uint8_t* ray_img[2] = {nullptr, nullptr};    //                       (tc::RW_END bytes)
+  uint8_t* view_img2[2] = {nullptr, nullptr};  // k_view_tc2 layout     (tc::V2_WEND bytes, ufo_view_tc2.cuh)
   ufo::ViewParams vp;
   ufo::RayParams rp;
 };
@@ -69,8 +70,6 @@ namespace ufo {
 // format and view-count group in ufo_tc_inst_*.cu.
 int tc_pass(bool bf16, const UfoScene* sc, const UfoWeights* w, int R, int half, const float* z, bool want_sim8,
             float* ray_out_tap, int sms, cudaStream_t st);
-int tc_pass_bf16_lo(const UfoScene*, const UfoWeights*, int, int, const float*, bool, float*, int, cudaStream_t);
-int tc_pass_bf16_hi(const UfoScene*, const UfoWeights*, int, int, const float*, bool, float*, int, cudaStream_t);
 int tc_pass_f16_lo(const UfoScene*, const UfoWeights*, int, int, const float*, bool, float*, int, cudaStream_t);
 int tc_pass_f16_hi(const UfoScene*, const UfoWeights*, int, int, const float*, bool, float*, int, cudaStream_t);
 }  // namespace ufo

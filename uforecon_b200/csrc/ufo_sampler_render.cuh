@@ -12,8 +12,9 @@ static __global__ void __launch_bounds__(256) k_ray_setup(SceneDev sc, const lon
                                                   long long ray_begin, int R, float* __restrict__ rayinfo) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R) return;
-  const long long pix = ray_idx ? ray_idx[r] : ray_begin + r;
   const long long HW = (long long)sc.H * sc.W;
+  long long pix = ray_idx ? ray_idx[r] : ray_begin + r;
+  pix = pix < 0 ? 0 : (pix >= HW ? HW - 1 : pix);      // memory safety for a caller-supplied index list (the host wrapper rejects it)
   const float cz = __ldg(sc.cam_ray_d + 2 * HW + pix);
   float* o = rayinfo + (size_t)r * 8;
   o[0] = __ldg(sc.ray_d + pix);

@@ -3,6 +3,8 @@
 #pragma once
 #include "ufo_handles.cuh"
 #include "ufo_xfmr_tc.cuh"
+#include "ufo_view_tc2.cuh"
+#include <cstdlib>
 
 namespace ufo {
 // One sample2rgb pass of the tensor-core pipeline over the R*64 points of half `half` (0: coarse samples,
@@ -19,7 +21,17 @@ static int launch_tc_pass(const UfoScene* sc, const UfoWeights* w, int R, int ha
   }
   UFO_KERNEL("k_gather_tc", st, k_gather_tc<NV, BF16><<<cdiv(P, 256), 256, gather_tc_smem<NV>(), st>>>(sc->d, ws.rayinfo, z, R, half, w->freqs, w->phases, w->pre_sim,
                                                                                   ws.tok, ws.rgbm, ws.dirs, want_sim8 ? ws.sim8 : nullptr));
-  {
+  static const int view_gen = getenv("UFO_VIEW_KERNEL") ? atoi(getenv("UFO_VIEW_KERNEL")) : 2;
+  static_assert(tc::V2_WEND == 141312, "k_view_tc2 weight image size (mirrored in ufo_api.cu)");
+  if (view_gen == 2) {     // two tiles in flight per CTA (ufo_view_tc2.cuh)
+    UFO_SMEM_ATTR((k_view_tc2<NV, BF16>), (int)tc::V2_SMEM);
+    constexpr int PPT = 4 * (32 / (NV + 1));
+    const long long tiles = (P + PPT - 1) / PPT;
+    const long long pairs = (tiles + 1) / 2;
+    const int grid = (int)(pairs < sms ? pairs : sms);
+    UFO_KERNEL("k_view_tc", st, k_view_tc2<NV, BF16><<<grid, 512, tc::V2_SMEM, st>>>(w->tc.view_img2[f], w->tc.vp, ws.tok, ws.rgbm, ws.dirs, (int)P, half,
+                                                                                    ws.vout0, ws.radiance));
+  } else {
     UFO_SMEM_ATTR((k_view_tc<NV, BF16>), (int)tc::V_SMEM);
     constexpr int PPT = 128 / (NV + 1);
     const long long tiles = (P + PPT - 1) / PPT;

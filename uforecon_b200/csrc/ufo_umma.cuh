@@ -22,25 +22,36 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// One try_wait.  -DUFO_MBAR_HINT adds a suspend-time hint (the warp sleeps in hardware until the phase completes or the
+// hint expires); measured on a B200 it wakes later than the plain form: k_ray_tc +2.5 %, k_view_tc2 +1.4 % - not the default.
 __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t"
       ".reg .pred P1;\n\t"
+#ifndef UFO_MBAR_HINT
       "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+#else
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+#endif
       "selp.u32 %0, 1, 0, P1;\n\t"
       "}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
       : "memory");
   return ok != 0;
 }
 // Bounded wait: a protocol error (a phase that never completes) traps after ~2 s instead of hanging the device.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) __trap();
+  long long t0 = 0;
+  for (uint32_t n = 1;; ++n) {
+    if (mbar_try(bar, parity)) return;
+    if ((n & 63u) == 0u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) __trap();
+    }
   }
 }
 // named barrier over `nthreads` threads (a multiple of 32); id 0 is __syncthreads

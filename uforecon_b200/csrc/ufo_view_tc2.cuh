@@ -1,0 +1,480 @@
+// View stage, second generation: TWO TILES IN FLIGHT per CTA.
+//
+//   LoFTREncoderLayer   code1/attention/transformer.py:35-58
+//   LinearAttention     code1/attention/linear_attention.py:20-47
+//   radiance head       code1/ray_transformer.py:159-163,310-320
+//
+// k_view_tc (ufo_xfmr_tc.cuh) runs one 128-row tile per CTA in lock step: MMA -> mbarrier wait -> fp32 epilogue ->
+// __syncthreads, seven times per tile; ncu showed the tensor pipe 17 % active and 39 % of the issue slots used.
+// Here the 512 threads are two independent halves of 256 threads.  Each half runs the whole per-tile program on its
+// own tile with its own 256 TMEM columns, its own mbarrier, its own issuing thread and a named barrier, so that one
+// half's MMAs and barrier waits are covered by the other half's epilogue arithmetic.  What makes two tiles fit:
+//   * every operand an epilogue produces (message, LayerNorm outputs, ReLU hidden layer, head side inputs) is written
+//     by its row owner straight into TMEM (tcgen05.st) and consumed as the A operand of a TS-form tcgen05.mma - no
+//     shared-memory staging, no fence.proxy.async, half the shared-memory bandwidth per MMA;
+//   * the per-point attention exchanges K'/V' between the L = NV+1 token rows of a point inside one warp (points are
+//     aligned to warps: floor(32/L) points per warp) through a 2.5 KB per-warp buffer, in fp32, one head at a time -
+//     no 16-bit staging tile, no CTA-wide barrier between the elu phase and the attention (warp shuffles were
+//     measured first: 2560 SHFL per tile, 19 % of the stall samples on the MIO queue);
+//   * the weights (138 KB) stay resident and are shared by both halves; the only activation operand in shared memory
+//     is the token tile X (A of the QKV GEMM, 20 KB), refilled by cp.async for the next tile as soon as the last MMA
+//     that reads it (mlp.0) has completed.
+// A thread owns one token row and one of TWO column groups (half of every accumulator row), so the fixed costs of a
+// phase (barriers, LayerNorm statistics, addressing) are paid by 8 warps per tile instead of 16.
+//
+// TMEM columns of a half (256): QKV [0,240) as [g0: q40 k40 v40 | g1: q40 k40 v40], radiance-head accumulator
+// [240,256).  Once QKV is consumed: message operand g0 [0,24) g1 [120,144) (40 values + 8 zeros = 3 K-steps each),
+// merge accumulator [144,224), LN1 operand [0,24) [24,48), mlp.0 accumulator [80,240), hidden operand [0,80),
+// mlp.2 accumulator [80,160), LN2 + direction/bias operand [0,24) [24,48).
+#pragma once
+#include "ufo_xfmr_tc.cuh"
+
+namespace ufo {
+namespace tc {
+// shared-memory map of k_view_tc2 (bytes); the weight block is also the layout of the global image
+constexpr uint32_t V2_WQKV = 0;                              // [240][80]   rows: g0 (q40 k40 v40) | g1 (q40 k40 v40)
+constexpr uint32_t V2_WMRG = V2_WQKV + 240 * 80 * 2;         // [80][96]    K: g0 40 | 0 x8 | g1 40 | 0 x8
+constexpr uint32_t V2_WML0 = V2_WMRG + 80 * 96 * 2;          // [160][176]  K: x 80 | message, padded like merge (96)
+constexpr uint32_t V2_WML2 = V2_WML0 + 160 * 176 * 2;        // [80][160]
+constexpr uint32_t V2_WRAD = V2_WML2 + 80 * 160 * 2;         // [16][176]   K: x 80 | LN2 g0 40 | dir 3, 1, 0 x4 | LN2 g1 40 | 0 x8
+constexpr uint32_t V2_WEND = V2_WRAD + 16 * 176 * 2;         // 141,312
+constexpr uint32_t V2H_X = 0;                                // per half: token operand, 10 chunks
+constexpr uint32_t V2H_XCH = 10 * kChunk;                    // per warp [32 rows][K' 10 | V 10] fp32: attention exchange of one head
+constexpr uint32_t V2H_RED = V2H_XCH + 8 * 2560;             // float2 [2][128] LayerNorm partials / float [2][128] head partials
+constexpr uint32_t V2H_RGBM = V2H_RED + 2 * 128 * 8;         // float4 [112]: (r,g,b,mask) of the tile's (point, view) pairs
+constexpr uint32_t V2H_SIZE = V2H_RGBM + 112 * 16;
+constexpr uint32_t V2_HALF = V2_WEND;
+constexpr uint32_t V2_BAR = V2_HALF + 2 * V2H_SIZE;
+constexpr uint32_t V2_SMEM = V2_BAR + 64;
+static_assert(V2_SMEM <= 232448, "view-stage (v2) shared memory exceeds the 227 KB opt-in limit");
+
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+#define UFO_G2_DISPATCH(fn)     \
+  if (g == 0) fn(IC<0>{});      \
+  else fn(IC<1>{});
+
+// LayerNorm partial (sum, sum of squares) of 40 accumulator columns starting at tcol
+__device__ __forceinline__ float2 ln40_load(uint32_t tcol, float2 (*v)[4]) {
+#pragma unroll
+  for (int i = 0; i < 5; ++i) tmem_ld8p(tcol + 8 * i, v[i]);
+  umma::tmem_ld_wait();
+  float2 s = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      s = __fadd2_rn(s, v[i][k]);
+      q2 = __ffma2_rn(v[i][k], v[i][k], q2);
+    }
+  return make_float2(s.x + s.y, q2.x + q2.y);
+}
+__device__ __forceinline__ float2 ln2_stats(const float2* red, int r, float inv_n) {
+  const float2 a0 = red[r], a1 = red[128 + r];
+  const float mean = (a0.x + a1.x) * inv_n;
+  const float var = fmaxf((a0.y + a1.y) * inv_n - mean * mean, 0.f);
+  return make_float2(mean, rsqrtf(var + 1e-5f));
+}
+}  // namespace tc
+
+template <int NV, bool BF16>
+__global__ void __launch_bounds__(512, 1)
+k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams prm, const uint16_t* __restrict__ tok,
+           const float4* __restrict__ rgbm, const float4* __restrict__ dirs, int P, int half, float* __restrict__ vout0,
+           float4* __restrict__ radiance) {
+  using namespace tc;
+  constexpr int L = NV + 1, PPW = 32 / L, PPT = 4 * PPW, RPW = PPW * L;   // points per warp / tile, rows in use per warp
+  static_assert(PPT * NV <= 112, "colour staging too small");
+  constexpr uint32_t FMT = BF16 ? umma::kFmtBF16 : umma::kFmtF16;
+  constexpr uint32_t D_QKV = 0, D_RAD = 240, D_MRG = 144, D_ML0 = 80, D_ML2 = 80;
+  extern __shared__ __align__(1024) uint8_t tc_smem[];
+  uint8_t* const smem = tc_smem;
+  const int tid = threadIdx.x, hf = tid >> 8, t = tid & 255, lane = tid & 31, wl = t >> 5;
+  const int q = wl & 3, g = wl >> 2, r = q * 32 + lane;
+  const int pl = q * PPW + lane / L, l = lane % L;
+  const bool row_ok = lane < RPW;
+  const int sl0 = (lane / L) * L;                       // first lane of this row's point
+  uint8_t* const hs = smem + V2_HALF + hf * V2H_SIZE;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + V2_BAR) + hf;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + V2_BAR + 32);
+  float2* red = reinterpret_cast<float2*>(hs + V2H_RED);
+  float* omg = reinterpret_cast<float*>(hs + V2H_RED);
+  float4* s_rgbm = reinterpret_cast<float4*>(hs + V2H_RGBM);
+  const uint32_t bar_id = 1 + hf;
+
+  if (tid < 32) umma::tmem_alloc(tmem_slot, 512);
+  if (tid == 0) {
+    umma::mbar_init(reinterpret_cast<uint64_t*>(smem + V2_BAR), 1);
+    umma::mbar_init(reinterpret_cast<uint64_t*>(smem + V2_BAR) + 1, 1);
+    umma::fence_barrier_init();
+  }
+  for (uint32_t i = tid; i < V2_WEND / 16; i += 512)
+    reinterpret_cast<uint4*>(smem)[i] = __ldg(reinterpret_cast<const uint4*>(wimg) + i);
+  // token operand buffers: row l == 0 of every point is the learnable view token (constant), unused rows are zero
+  for (int i = tid; i < 2 * 1280; i += 512) {
+    const int hb = i / 1280, j = i - hb * 1280;          // half, piece
+    const int rr = j & 127, c = j >> 7;
+    const int ln = rr & 31;
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = (ln < RPW && (ln % L) == 0) ? prm.vtok[c * 8 + k] : 0.f;
+    st_chunk<BF16>(smem + V2_HALF + hb * V2H_SIZE + V2H_X, rr, c, v);
+  }
+  umma::fence_async_smem();
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tm = *tmem_slot + 256u * hf;
+  const uint32_t tl = tm + ((uint32_t)(q * 32) << 16);
+  const uint32_t sm_base = umma::smem_u32(smem);
+  const uint32_t x_base = umma::smem_u32(hs + V2H_X);
+  const uint32_t G = 120u * g;
+  uint32_t ph = 0;
+  const int n_tiles = (P + PPT - 1) / PPT;
+  const int tstep = 2 * gridDim.x;
+  auto slot_of = [&](int p) -> int { return (p >> 6) * kNS + half * kNC + (p & 63); };
+
+  // token rows of a tile -> X[buf] by cp.async: piece i = (row rr, chunk c); rows of the view token stay as initialised
+  auto load_tokens = [&](int tile) {
+    const int pbase = tile * PPT;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int i = t + k * 256;
+      const int rr = i & 127, c = i >> 7;
+      const int ln = rr & 31;
+      const int ll = ln % L;
+      const int p = pbase + (rr >> 5) * PPW + ln / L;
+      if (ln < RPW && ll > 0 && p < P)
+        cp_async16(x_base + c * kChunk + rr * 16,
+                   tok + (size_t)slot_of(p) * (NV * kDView) + (ll - 1) * kDView + c * 8);
+    }
+    cp_async_commit();
+  };
+  // wait for this half's last commit: with UFO_VIEW_POLL1 one warp polls the mbarrier and releases the others through the
+  // named barrier (the other seven warps then block without using issue slots)
+  auto half_wait = [&]() {
+#ifdef UFO_VIEW_POLL1
+    if (wl == 0) umma::mbar_wait(bar, ph);
+    umma::bar_sync(bar_id, 256);
+#else
+    umma::mbar_wait(bar, ph);
+#endif
+    ph ^= 1;
+    umma::tc_fence_after();
+  };
+  int tile = 2 * blockIdx.x + hf;
+  if (tile < n_tiles) load_tokens(tile);
+  float4* const xw = reinterpret_cast<float4*>(hs + V2H_XCH + wl * 2560);   // this warp's exchange buffer [32][5] float4
+
+  for (; tile < n_tiles; tile += tstep) {
+    const int pbase = tile * PPT;
+    const int my_p = pbase + pl;
+    const size_t my_slot = (size_t)slot_of(my_p);
+    const bool live = row_ok && my_p < P;
+    const uint32_t xb = x_base;
+    // ---- P0: this tile's token rows have landed
+    cp_async_wait_all();
+    umma::fence_async_smem();
+    umma::tc_fence_before();
+    umma::bar_sync(bar_id, 256);
+    // ---- P1: q|k|v = X . Wqkv^T (transformer.py:47) and the x part of the radiance head's first layer
+    if (t == 0) {
+      umma::tc_fence_after();
+      issue_gemm_sub(tm + D_QKV, xb, sm_base + V2_WQKV, 240, 0, 10, umma::make_idesc(128, 240, FMT, false, false), 0);
+      umma::commit(bar);
+      issue_gemm_sub(tm + D_RAD, xb, sm_base + V2_WRAD, 16, 0, 10, umma::make_idesc(128, 16, FMT, false, false), 0);
+    }
+    float3 my_dir = make_float3(0.f, 0.f, 0.f);
+    if (live && l > 0 && g == 0) {
+      const float* dp = reinterpret_cast<const float*>(dirs + my_slot * NV + (l - 1));
+      const float2 dxy = __ldg(reinterpret_cast<const float2*>(dp));
+      my_dir.x = dxy.x;
+      my_dir.y = dxy.y;
+      my_dir.z = __ldg(dp + 2);
+    }
+    float4 my_col = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < PPT * NV) {
+      const int pp = pbase + t / NV;
+      if (pp < P) my_col = __ldg(rgbm + (size_t)slot_of(pp) * NV + (t % NV));
+    }
+    half_wait();
+    // ---- P2+P3: elu+1 on q, k; msg_l = sum_s (Q_l.K_s) V_s / (sum_s Q_l.K_s + 1e-6) per head over the L token rows of
+    //      the point (== Q (K^T V) Z, linear_attention.py:36-45), K'/V' of the other rows by warp shuffle.
+    //      Thread (row, g) owns heads 4g .. 4g+3 = columns [120g, 120g+120) of the accumulator.
+    {
+      uint32_t mo[24];
+#pragma unroll
+      for (int hp = 0; hp < 2; ++hp) {
+        float qf[20], kf[20], vf[20];
+        const uint32_t c0 = tl + D_QKV + G + 20 * hp;
+        umma::tmem_ld16(c0, qf);
+        tmem_ld4(c0 + 16, qf + 16);
+        umma::tmem_ld16(c0 + 40, kf);
+        tmem_ld4(c0 + 56, kf + 16);
+        umma::tmem_ld16(c0 + 80, vf);
+        tmem_ld4(c0 + 96, vf + 16);
+        umma::tmem_ld_wait();
+        float2 q2[10], k2[10];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+          q2[i] = elu1_2(make_float2(qf[2 * i], qf[2 * i + 1]));
+          k2[i] = elu1_2(make_float2(kf[2 * i], kf[2 * i + 1]));
+        }
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          // this row's K' | V of the head -> the warp's exchange buffer (80 B rows: conflict-free 16-byte stores)
+          __syncwarp();                                         // the previous head's readers are done
+          xw[lane * 5 + 0] = make_float4(k2[5 * hh].x, k2[5 * hh].y, k2[5 * hh + 1].x, k2[5 * hh + 1].y);
+          xw[lane * 5 + 1] = make_float4(k2[5 * hh + 2].x, k2[5 * hh + 2].y, k2[5 * hh + 3].x, k2[5 * hh + 3].y);
+          xw[lane * 5 + 2] = make_float4(k2[5 * hh + 4].x, k2[5 * hh + 4].y, vf[10 * hh], vf[10 * hh + 1]);
+          xw[lane * 5 + 3] = make_float4(vf[10 * hh + 2], vf[10 * hh + 3], vf[10 * hh + 4], vf[10 * hh + 5]);
+          xw[lane * 5 + 4] = make_float4(vf[10 * hh + 6], vf[10 * hh + 7], vf[10 * hh + 8], vf[10 * hh + 9]);
+          __syncwarp();
+          float2 msg[5];
+#pragma unroll
+          for (int b = 0; b < 5; ++b) msg[b] = make_float2(0.f, 0.f);
+          float den = 0.f;
+#pragma unroll
+          for (int s = 0; s < L; ++s) {
+            const float4* src = xw + ((sl0 + s) & 31) * 5;     // the same address for the L rows of a point: broadcast
+            const float4 a0 = src[0], a1 = src[1], a2 = src[2], a3 = src[3], a4 = src[4];
+            float2 acc = __fmul2_rn(q2[5 * hh], make_float2(a0.x, a0.y));
+            acc = __ffma2_rn(q2[5 * hh + 1], make_float2(a0.z, a0.w), acc);
+            acc = __ffma2_rn(q2[5 * hh + 2], make_float2(a1.x, a1.y), acc);
+            acc = __ffma2_rn(q2[5 * hh + 3], make_float2(a1.z, a1.w), acc);
+            acc = __ffma2_rn(q2[5 * hh + 4], make_float2(a2.x, a2.y), acc);
+            const float sc = acc.x + acc.y;
+            den += sc;
+            const float2 sc2 = make_float2(sc, sc);
+            msg[0] = __ffma2_rn(sc2, make_float2(a2.z, a2.w), msg[0]);
+            msg[1] = __ffma2_rn(sc2, make_float2(a3.x, a3.y), msg[1]);
+            msg[2] = __ffma2_rn(sc2, make_float2(a3.z, a3.w), msg[2]);
+            msg[3] = __ffma2_rn(sc2, make_float2(a4.x, a4.y), msg[3]);
+            msg[4] = __ffma2_rn(sc2, make_float2(a4.z, a4.w), msg[4]);
+          }
+          const float zi = 1.f / (den + 1e-6f);
+          const float2 z2 = make_float2(zi, zi);
+#pragma unroll
+          for (int b = 0; b < 5; ++b) mo[10 * hp + 5 * hh + b] = pack2v<BF16>(__fmul2_rn(msg[b], z2));
+        }
+      }
+      mo[20] = mo[21] = mo[22] = mo[23] = 0u;
+      // message operand of this group: its own (consumed) q columns [120g, 120g+24)
+      umma::tmem_st8(tl + G, mo);
+      umma::tmem_st8(tl + G + 8, mo + 8);
+      umma::tmem_st8(tl + G + 16, mo + 16);
+      umma::tmem_st_wait();
+    }
+    umma::tc_fence_before();
+    umma::bar_sync(bar_id, 256);
+    // ---- P4: merge (transformer.py:55), A from TMEM
+    if (t == 0) {
+      umma::tc_fence_after();
+      const uint32_t idesc = umma::make_idesc(128, 80, FMT, false, false);
+      constexpr uint32_t lbo = 80 * 16;
+#pragma unroll
+      for (int ks = 0; ks < 6; ++ks)
+        umma::mma_f16_ts(tm + D_MRG, tm + 120 * (ks / 3) + 8 * (ks % 3), umma::make_smem_desc(sm_base + V2_WMRG + 2 * ks * lbo, lbo, 128u),
+                         idesc, ks > 0);
+      umma::commit(bar);
+    }
+    if (t < PPT * NV) s_rgbm[t] = my_col;
+    half_wait();
+    // ---- P5: LayerNorm 1 (transformer.py:56) -> message half of the mlp.0 operand, columns [24g, 24g+24)
+    {
+      auto ln1 = [&](auto GGc) {
+        constexpr int GG = decltype(GGc)::value;
+        float2 v[5][4];
+        red[GG * 128 + r] = ln40_load(tl + D_MRG + 40 * GG, v);
+        umma::tc_fence_before();
+        umma::bar_sync(bar_id, 256);
+        if (GG == 0 && t == 0) {   // the merge accumulator is consumed: the x half of mlp.0 runs under the rest of this phase
+          umma::tc_fence_after();
+          issue_gemm_sub(tm + D_ML0, xb, sm_base + V2_WML0, 160, 0, 10, umma::make_idesc(128, 160, FMT, false, false), 0);
+        }
+        const float2 st = ln2_stats(red, r, 1.f / 80.f);
+        uint32_t o[24];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          float2 y[4];
+          ln_apply(v[i], st, prm.n1w + 40 * GG + 8 * i, prm.n1b + 40 * GG + 8 * i, y);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) o[4 * i + k] = pack2v<BF16>(y[k]);
+        }
+        o[20] = o[21] = o[22] = o[23] = 0u;
+        umma::tmem_st8(tl + 24 * GG, o);
+        umma::tmem_st8(tl + 24 * GG + 8, o + 8);
+        umma::tmem_st8(tl + 24 * GG + 16, o + 16);
+        umma::tmem_st_wait();
+      };
+      UFO_G2_DISPATCH(ln1)
+    }
+    umma::tc_fence_before();
+    umma::bar_sync(bar_id, 256);
+    // ---- P6: mlp.0 on [x | LN1]  (transformer.py:57): message half from TMEM on top of the x half issued inside P5
+    if (t == 0) {
+      umma::tc_fence_after();
+      const uint32_t idesc = umma::make_idesc(128, 160, FMT, false, false);
+      constexpr uint32_t lbo = 160 * 16;
+#pragma unroll
+      for (int ks = 0; ks < 6; ++ks)
+        umma::mma_f16_ts(tm + D_ML0, tm + 24 * (ks / 3) + 8 * (ks % 3),
+                         umma::make_smem_desc(sm_base + V2_WML0 + (10 + 2 * ks) * lbo, lbo, 128u), idesc, 1u);
+      umma::commit(bar);
+    }
+    half_wait();
+    if (tile + tstep < n_tiles) load_tokens(tile + tstep);     // X is free: mlp.0 was the last MMA reading it
+    // ---- P7: ReLU -> hidden operand [40g, 40g+40)
+    {
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        float2 v[5][4];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) tmem_ld8p(tl + D_ML0 + 80 * g + 40 * b + 8 * i, v[i]);
+        umma::tmem_ld_wait();
+        uint32_t o[20];
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) o[4 * i + k] = relu_pack2<BF16>(v[i][k]);
+        umma::tmem_st8(tl + 40 * g + 20 * b, o);
+        umma::tmem_st8(tl + 40 * g + 20 * b + 8, o + 8);
+        umma::tmem_st4(tl + 40 * g + 20 * b + 16, o[16], o[17], o[18], o[19]);
+      }
+      umma::tmem_st_wait();
+    }
+    umma::tc_fence_before();
+    umma::bar_sync(bar_id, 256);
+    // ---- P8: mlp.2
+    if (t == 0) {
+      umma::tc_fence_after();
+      const uint32_t idesc = umma::make_idesc(128, 80, FMT, false, false);
+      constexpr uint32_t lbo = 80 * 16;
+#pragma unroll
+      for (int ks = 0; ks < 10; ++ks)
+        umma::mma_f16_ts(tm + D_ML2, tm + 8 * ks, umma::make_smem_desc(sm_base + V2_WML2 + 2 * ks * lbo, lbo, 128u), idesc, ks > 0);
+      umma::commit(bar);
+    }
+    half_wait();
+    // ---- P9: LayerNorm 2; token 0: out = view_token + LN2 -> vout0 (fp32); view rows: LN2 (+ direction, 1) -> operand of the
+    //      radiance head (x + LN2 is applied inside the head's GEMM: W0x.x + W0x.LN2)
+    {
+      auto ln2 = [&](auto GGc) {
+        constexpr int GG = decltype(GGc)::value;
+        float2 v[5][4];
+        red[GG * 128 + r] = ln40_load(tl + D_ML2 + 40 * GG, v);
+        umma::bar_sync(bar_id, 256);
+        const float2 st = ln2_stats(red, r, 1.f / 80.f);
+        const bool tok0 = live && l == 0;
+        uint32_t o[24];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          float2 y[4];
+          const int c = 40 * GG + 8 * i;
+          ln_apply(v[i], st, prm.n2w + c, prm.n2b + c, y);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) o[4 * i + k] = pack2v<BF16>(y[k]);
+          if (tok0) {
+            float4* dst = reinterpret_cast<float4*>(vout0 + my_slot * kDView + c);
+            dst[0] = make_float4(prm.vtok[c] + y[0].x, prm.vtok[c + 1] + y[0].y, prm.vtok[c + 2] + y[1].x, prm.vtok[c + 3] + y[1].y);
+            dst[1] = make_float4(prm.vtok[c + 4] + y[2].x, prm.vtok[c + 5] + y[2].y, prm.vtok[c + 6] + y[3].x, prm.vtok[c + 7] + y[3].y);
+          }
+        }
+        if (GG == 0) {        // side inputs of the head: relative direction and the constant 1 that carries the bias
+          o[20] = umma::pack2<BF16>(my_dir.x, my_dir.y);
+          o[21] = umma::pack2<BF16>(my_dir.z, 1.f);
+          o[22] = o[23] = 0u;
+        } else {
+          o[20] = o[21] = o[22] = o[23] = 0u;
+        }
+        umma::tmem_st8(tl + 24 * GG, o);
+        umma::tmem_st8(tl + 24 * GG + 8, o + 8);
+        umma::tmem_st8(tl + 24 * GG + 16, o + 16);
+        umma::tmem_st_wait();
+      };
+      UFO_G2_DISPATCH(ln2)
+    }
+    umma::tc_fence_before();
+    umma::bar_sync(bar_id, 256);
+    // ---- P10: LN2 / direction / bias part of the radiance head's first layer   (ray_transformer.py:159-163,313)
+    if (t == 0) {
+      umma::tc_fence_after();
+      const uint32_t idesc = umma::make_idesc(128, 16, FMT, false, false);
+      constexpr uint32_t lbo = 16 * 16;
+#pragma unroll
+      for (int ks = 0; ks < 6; ++ks)
+        umma::mma_f16_ts(tm + D_RAD, tm + 24 * (ks / 3) + 8 * (ks % 3),
+                         umma::make_smem_desc(sm_base + V2_WRAD + (10 + 2 * ks) * lbo, lbo, 128u), idesc, 1u);
+      umma::commit(bar);
+    }
+    half_wait();
+    // ---- P11: head tail 16 -> 8 -> 1 (hidden units 4g .. 4g+3 per thread), masked softmax over views, colour blend
+    {
+      float h[16];
+      umma::tmem_ld16(tl + D_RAD, h);
+      umma::tmem_ld_wait();
+      auto tail = [&](auto GGc) {
+        constexpr int GG = decltype(GGc)::value;
+#pragma unroll
+        for (int o = 0; o < 16; ++o) h[o] = fmaxf(h[o], 0.f);      // bias and direction terms came through the GEMM
+        float part = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int o = 4 * GG + j;
+          float a0 = prm.rb2[o], a1 = 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            a0 = fmaf(h[i], prm.rw2[o][i], a0);
+            a1 = fmaf(h[i + 1], prm.rw2[o][i + 1], a1);
+          }
+          part = fmaf(fmaxf(a0 + a1, 0.f), prm.rw4[o], part);
+        }
+        omg[GG * 128 + r] = part;
+      };
+      UFO_G2_DISPATCH(tail)
+    }
+    umma::tc_fence_before();
+    umma::bar_sync(bar_id, 256);
+    if (t < PPT && pbase + t < P) {
+      const size_t p = (size_t)slot_of(pbase + t);
+      const int rr0 = (t / PPW) * 32 + (t % PPW) * L + 1;        // row of (point t, view 0)
+      float om[NV];
+      float4 col[NV];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int n = 0; n < NV; ++n) {
+        col[n] = s_rgbm[t * NV + n];
+        const float w = prm.rb4 + (omg[rr0 + n] + omg[128 + rr0 + n]);
+        om[n] = (col[n].w == 0.f) ? -1e9f : w;                     // ray_transformer.py:316
+        mx = fmaxf(mx, om[n]);
+      }
+      float den = 0.f;
+#pragma unroll
+      for (int n = 0; n < NV; ++n) {
+        om[n] = ex2_ftz((om[n] - mx) * 1.4426950408889634f);
+        den += om[n];
+      }
+      float cr = 0.f, cg = 0.f, cb = 0.f;
+#pragma unroll
+      for (int n = 0; n < NV; ++n) {
+        const float pw = om[n] / den;
+        cr = fmaf(col[n].x, pw, cr);
+        cg = fmaf(col[n].y, pw, cg);
+        cb = fmaf(col[n].z, pw, cb);
+      }
+      radiance[p] = make_float4(cr, cg, cb, 0.f);
+    }
+    // omg / s_rgbm are next written after several more barriers of this half; the next tile's QKV MMA overwrites TMEM only
+    // after its P0 barrier, which every thread reaches after its last TMEM read above
+  }
+  cp_async_wait_all();
+  umma::tc_fence_before();
+  __syncthreads();
+  if (tid < 32) umma::tmem_dealloc(*tmem_slot, 512);
+}
+
+}  // namespace ufo

@@ -44,10 +44,16 @@ class HotPathWeights:
         self.device = torch.device(device if device is not None else "cuda")
         keep: List[torch.Tensor] = []
 
+        self.max_abs_weight = 0.0
+
         def p(name: str) -> int:
             if name not in state_dict:
                 raise KeyError(f"state dict lacks hot-path key {name!r}")
             t = _host_f32(state_dict[name])
+            if not bool(torch.isfinite(t).all()):
+                raise ValueError(f"hot-path tensor {name!r} holds non-finite values")
+            if name.endswith("weight") and t.numel():
+                self.max_abs_weight = max(self.max_abs_weight, float(t.abs().max()))
             keep.append(t)
             return t.data_ptr()
 
@@ -76,6 +82,12 @@ class HotPathWeights:
         d.depth_freqs = p(RT + "depthcode._freqs")
         d.depth_phases = p(RT + "depthcode._phases")
         d.variance = float(state_dict["deviation_network.variance"])
+        # the tensor-core mode packs operands in fp16 (saturating at +-65504, 11-bit mantissa): weights far outside the
+        # xavier scale it was validated on would clip or lose their small entries - say so instead of doing it silently
+        if self.max_abs_weight > 1024.0:
+            import warnings
+            warnings.warn(f"hot-path weights reach |w| = {self.max_abs_weight:.3g}: UFO_MODE_TC_F16 packs operands in fp16 "
+                          f"(validated on |w| <~ 1 only); check the result against UFO_MODE_FP32", RuntimeWarning)
         self.handle = C.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(self.lib.ufo_weights_create(C.byref(d), C.byref(self.handle), _stream_ptr(self.device)))
@@ -110,6 +122,28 @@ class Scene:
             raise ValueError(f"match_feature[0] shape {tuple(match_feature[0].shape)} != {(1, NV, (NV - 1) * 32, h, w)}")
         if "depth_info" not in batch:
             raise KeyError("batch['depth_info'] missing (set by extract_geometry, model.py:806-808)")
+        # every tensor the kernels index with NV / H*W strides is checked here: the library trusts these shapes
+        # (the reference's grid_sample would resample a mismatched map; the fused kernels would read out of bounds)
+        s_idx = batch.get("start_idx", 1)                     # ray_transformer.py:182: 0 in inference batches, 1 in training ones
+        s_idx = int(s_idx.item()) if torch.is_tensor(s_idx) else int(s_idx)
+
+        def need(name, t, shape):
+            if tuple(t.shape) != tuple(shape):
+                raise ValueError(f"{name} shape {tuple(t.shape)} != {tuple(shape)}")
+
+        need("batch['source_imgs']", batch["source_imgs"], (1, NV, 3, H, W))
+        need("source_imgs_feat", source_imgs_feat, (1, NV, 32, h, w))
+        need("batch['depth_info']", batch["depth_info"], (1, NV, H, W))
+        need("batch['ray_d']", batch["ray_d"], (1, 3, H * W))
+        need("batch['cam_ray_d']", batch["cam_ray_d"], (1, 3, H * W))
+        need("batch['ray_o']", batch["ray_o"], (1, 3))
+        need("batch['ref_pose_inv']", batch["ref_pose_inv"], (1, 4, 4))
+        need("batch['source_poses']", batch["source_poses"], (1, NV, 4, 4))
+        need("batch['source_poses_inv']", batch["source_poses_inv"], (1, NV, 4, 4))
+        if batch["w2cs"].dim() != 4 or batch["w2cs"].shape[0] != 1 or batch["w2cs"].shape[1] < s_idx + NV or tuple(batch["w2cs"].shape[2:]) != (4, 4):
+            raise ValueError(f"batch['w2cs'] shape {tuple(batch['w2cs'].shape)}: need [1, >= start_idx + {NV}, 4, 4] (start_idx = {s_idx})")
+        if batch["near_fars"].dim() != 3 or batch["near_fars"].shape[0] != 1 or batch["near_fars"].shape[1] < 1 or batch["near_fars"].shape[2] != 2:
+            raise ValueError(f"batch['near_fars'] shape {tuple(batch['near_fars'].shape)}: need [1, >= 1, 2]")
         dev = self.device
         keep = []
 
@@ -131,14 +165,14 @@ class Scene:
         d.match_feats = dv(match_feature[0][0])
         for i, st in enumerate(STAGES):
             fv, wv = feature_volume[st]["feature_volume"], feature_volume[st]["weight_volume"]
-            if fv.shape[0] != NV or fv.shape[1] != 8 or wv.shape[1] != 1:
-                raise ValueError(f"{st}: feature/weight volume shapes {tuple(fv.shape)} / {tuple(wv.shape)}")
+            if fv.dim() != 5 or wv.dim() != 5 or fv.shape[0] != NV or fv.shape[1] != 8 or tuple(wv.shape) != (NV, 1) + tuple(fv.shape[2:]):
+                raise ValueError(f"{st}: feature/weight volume shapes {tuple(fv.shape)} / {tuple(wv.shape)}: need [{NV},8,D,h,w] / [{NV},1,D,h,w]")
             d.vol_feat[i], d.vol_weight[i] = dv(fv), dv(wv)
             d.vol_d[i], d.vol_h[i], d.vol_w[i] = fv.shape[2], fv.shape[3], fv.shape[4]
         d.source_poses = hv(batch["source_poses"][0])
         d.source_poses_inv = hv(batch["source_poses_inv"][0])
         d.ref_pose_inv = hv(batch["ref_pose_inv"][0])
-        d.w2cs = hv(batch["w2cs"][0])
+        d.w2cs = hv(batch["w2cs"][0][s_idx:s_idx + NV])      # ray_transformer.py:240: w2cs[:, s_idx:]
         d.near_fars = hv(batch["near_fars"][0])
         d.ray_o = hv(batch["ray_o"][0])
         d.ray_d = dv(batch["ray_d"][0])
@@ -205,6 +239,10 @@ def render_rays(scene: Scene, weights: HotPathWeights, ray_idx: Optional[torch.T
         ray_idx = ray_idx.detach().to(dev, torch.int64).contiguous()
         if ray_idx.numel() != n_rays:
             raise ValueError("ray_idx size != n_rays")
+        if n_rays > 0:
+            lo, hi = torch.aminmax(ray_idx)
+            if int(lo) < 0 or int(hi) >= scene.H * scene.W:
+                raise ValueError(f"ray_idx values [{int(lo)}, {int(hi)}] outside the {scene.H}x{scene.W} ray grid")
         idx_ptr = ray_idx.data_ptr()
     with torch.cuda.device(dev):
         _lib.check(lib.ufo_render_rays(scene.handle, weights.handle, idx_ptr, ray_begin, n_rays, u_c.data_ptr(), u_f.data_ptr(),
@@ -217,24 +255,61 @@ class UFOReconRenderer:
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], device=None, mode: int = UFO_MODE_TC_F16,
                  test_ray_num: int = 800):
-        # default = fp16 operands: same speed as bf16 (UFO_MODE_TC) and inside the north-star tolerance at the full
-        # 1600x1216 size, where bf16's 8-bit mantissa is not (tests/test_gpu_fullsize.py); packing saturates at +-65504
+        # default = tensor cores with fp16 operands: inside the north-star tolerance at the full 1600x1216 size
+        # (tests/test_gpu_fullsize.py); operand packing saturates at +-65504 (validated on synthetic xavier-scale weights
+        # only - the pretrained checkpoint is not available offline; HotPathWeights warns about weights outside fp16 range)
         self.device = torch.device(device if device is not None else "cuda")
         self.weights = HotPathWeights(state_dict, self.device)
         self.mode = mode
         self.test_ray_num = test_ray_num
         self._scene_key = None
         self._scene: Optional[Scene] = None
+        self._scene_refs = None
+        self._pinned_scene: Optional[Scene] = None
+
+    @staticmethod
+    def _scene_inputs(batch, source_imgs_feat, feature_volume, match_feature):
+        """Every tensor a Scene bakes in (not only the encoder outputs: the render view's rays, poses and MVS depth too)."""
+        ts = [source_imgs_feat, match_feature[0]]
+        for st in STAGES:
+            ts += [feature_volume[st]["feature_volume"], feature_volume[st]["weight_volume"]]
+        for k in ("source_imgs", "depth_info", "source_poses", "source_poses_inv", "ref_pose_inv", "w2cs", "near_fars", "ray_o",
+                  "ray_d", "cam_ray_d", "scale_mat"):
+            if k in batch and torch.is_tensor(batch[k]):
+                ts.append(batch[k])
+        return ts
 
     def _scene_for(self, batch, source_imgs_feat, feature_volume, match_feature) -> Scene:
-        key = (source_imgs_feat.data_ptr(), match_feature[0].data_ptr(), batch["source_poses"].data_ptr(),
-               feature_volume["stage3"]["feature_volume"].data_ptr())
+        """The Scene of this call's inputs, rebuilt whenever ANY consumed tensor is another object or was written in place.
+
+        Identity is (object id, in-place version counter) per tensor, and the cached entry keeps the tensors alive, so neither
+        an address handed out again by the caching allocator nor an in-place update of the encoder outputs can alias a
+        stale Scene (consecutive ``extract_geometry`` batches of one scan share the source views and differ in the render
+        view's rays / poses only).  ``begin_scene`` / ``end_scene`` give the caller explicit control instead.
+        """
+        if self._pinned_scene is not None:
+            return self._pinned_scene
+        ts = self._scene_inputs(batch, source_imgs_feat, feature_volume, match_feature)
+        s_idx = batch.get("start_idx", 1)
+        key = tuple((id(t), t._version) for t in ts) + (int(s_idx.item()) if torch.is_tensor(s_idx) else int(s_idx),)
         if self._scene is None or key != self._scene_key:
             if self._scene is not None:
                 self._scene.close()
             self._scene = Scene(batch, source_imgs_feat, feature_volume, match_feature, self.device)
             self._scene_key = key
+            self._scene_refs = ts                      # keeps ids / addresses from being reused while cached
         return self._scene
+
+    def begin_scene(self, batch, source_imgs_feat, feature_volume, match_feature) -> Scene:
+        """Explicit scope: build the Scene of one ``extract_geometry`` call; ``infer`` / ``render_depth_map`` use it until ``end_scene``."""
+        self.end_scene()
+        self._pinned_scene = Scene(batch, source_imgs_feat, feature_volume, match_feature, self.device)
+        return self._pinned_scene
+
+    def end_scene(self):
+        if self._pinned_scene is not None:
+            self._pinned_scene.close()
+            self._pinned_scene = None
 
     def infer(self, batch, ray_idx, source_imgs_feat, feature_volume=None, extract_geometry=False, match_feature=None,
               ray_idx_all=None, is_train=True):
@@ -284,7 +359,9 @@ class UFOReconRenderer:
         return depth_mm, r["rgb"].view(H, W, 3)
 
     def close(self):
+        self.end_scene()
         if self._scene is not None:
             self._scene.close()
             self._scene = None
+            self._scene_refs = None
         self.weights.close()
