@@ -216,6 +216,14 @@ int ufo_costvolume_stage(const float* const* feats, int32_t n_rot, int32_t n_vie
                          const float* depth_hyp, const float* view_w_in, const UfoPixelwiseNet* pw,
                          float* similarity, float* view_w_out, void* stream);
 
+/* The same stage with the homographies supplied by the caller: rot_trans [host] [N][V-1][12] = rot (3x3, row-major) then
+ * trans (3) of src_proj_new . inverse(ref_proj_new), built the way the reference builds them (fp32 torch.matmul /
+ * torch.inverse, TransMVSNet.py:77-81, fmt/module.py:340-342) so that the warp coordinates agree with the reference's to
+ * rounding.  ufo_costvolume_stage derives them from proj in double instead. */
+int ufo_costvolume_stage_rt(const float* const* feats, int32_t N, int32_t V, int32_t C, int32_t h, int32_t w,
+                            int32_t D, const float* rot_trans, const float* depth_hyp, const float* view_w_in,
+                            const UfoPixelwiseNet* pwn, float* sim_out, float* view_w_out, void* stream);
+
 /* Alternative feature grid of --volume_type featuregrid (row a19): FeatureVolume.forward up to its 3-D regulariser
  * (code1/feature_volume.py:40-92).  feats [dev] [NV,32,h,w]; source_poses [host] [NV,4,4] world->NDC; linear = the
  * module's nn.Sequential (32->32 ReLU, 32->16 ReLU, 16->8; torch [out,in] layout, host); out [dev] [16,reso,reso,reso]

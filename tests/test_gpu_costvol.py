@@ -22,12 +22,30 @@ def test_costvolume_cascade_matches_reference():
         sim, vw_new = similarity_volume(feats, proj, hyp, sd, view_weights=vw)
         with torch.no_grad():
             o_sim, o_vw = orc.cost_volume_stage(feats, proj, hyp, sd, view_weights=vw.cpu() if vw is not None else None)
-        # 1e-5 of the volume's scale; a handful of voxels sit on a bilinear tap boundary where the
-        # double-precision warp matrices of the library and torch's fp32 inverse pick different texels
-        err = (sim.cpu() - o_sim).abs() / o_sim.abs().max()
-        assert float((err > 1e-5).float().mean()) < 1e-4, (stage, float(err.max()))
-        assert float(err.max()) < 5e-3, stage
-        assert rel_err(sim.cpu(), g[f"{stage}_sim"]) < 5e-3
+        # the homographies are built on the host exactly as the reference builds them (fp32 torch.inverse / matmul,
+        # uforecon_b200/costvolume.py), so the warp coordinates agree to rounding: 1e-5 of the volume's scale for EVERY
+        # voxel, against the oracle and against the reference's own output (tests/golden/costvol_nv3.npz)
+        assert rel_err(sim.cpu(), o_sim) <= 1e-5, (stage, rel_err(sim.cpu(), o_sim))
+        assert rel_err(sim.cpu(), g[f"{stage}_sim"]) <= 1e-5, (stage, rel_err(sim.cpu(), g[f"{stage}_sim"]))
         if si == 0:
             assert rel_err(vw_new.cpu(), o_vw) <= 1e-4
         vw = vw_new.cpu()
+
+
+def test_costvolume_stage3_at_baseline_size():
+    """Stage 3 (C=8, D=8, full resolution) of the 1600x1216 NV=3 cascade, one reference rotation: same 1e-5 bar against the
+    oracle (the warped volume the oracle materialises is 1.5 GB per source view, so one rotation keeps the test short)."""
+    from uforecon_b200.costvolume import similarity_volume
+    from uforecon_b200 import synthetic
+    batch, sd, stages = costvol_inputs(synthetic.UNFAVORABLE_VIEWS, (1600, 1216))
+    stage, feats, proj, hyp = stages[2]
+    feats = [f[:1].contiguous() for f in feats]
+    proj, hyp = proj[:1].contiguous(), hyp[:1].contiguous()
+    g = torch.Generator().manual_seed(3)
+    vw = torch.rand(1, 2, 1216, 1600, generator=g)
+    sim, _ = similarity_volume(feats, proj, hyp, sd, view_weights=vw)
+    with torch.no_grad():
+        o_sim, _ = orc.cost_volume_stage(feats, proj, hyp, sd, view_weights=vw)
+    e = rel_err(sim.cpu(), o_sim)
+    print(f"stage3 1600x1216: max err / max|ref| = {e:.2e} over {o_sim.numel()} voxels")
+    assert tuple(sim.shape) == (1, 1, 8, 1216, 1600) and e <= 1e-5

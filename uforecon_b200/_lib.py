@@ -82,7 +82,7 @@ class UfoProfileEntry(C.Structure):
 EXPORTS = (
     "ufo_abi_version", "ufo_last_error", "ufo_device_info", "ufo_weights_create", "ufo_weights_destroy",
     "ufo_scene_create", "ufo_scene_destroy", "ufo_scene_device_bytes", "ufo_render_rays", "ufo_render_rays_host",
-    "ufo_launch_count", "ufo_costvolume_stage", "ufo_debug_umma_selftest", "ufo_profile_begin", "ufo_profile_end",
+    "ufo_launch_count", "ufo_costvolume_stage", "ufo_costvolume_stage_rt", "ufo_debug_umma_selftest", "ufo_profile_begin", "ufo_profile_end",
     "ufo_tsdf_integrate", "ufo_feature_grid", "ufo_tsdf_mesh_begin", "ufo_tsdf_mesh_emit", "ufo_tsdf_mesh_destroy",
 )
 
@@ -121,6 +121,7 @@ def load() -> C.CDLL:
     lib.ufo_costvolume_stage.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                          C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(UfoPixelwiseNet),
                                          C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ufo_costvolume_stage_rt.argtypes = lib.ufo_costvolume_stage.argtypes
     lib.ufo_debug_umma_selftest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                             C.c_void_p]
     lib.ufo_tsdf_integrate.argtypes = [C.POINTER(UfoTsdfGrid), C.c_void_p, C.c_void_p, C.POINTER(UfoTsdfView), C.c_int32, C.c_float,

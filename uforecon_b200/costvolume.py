@@ -50,7 +50,20 @@ def similarity_volume(features: Sequence[torch.Tensor], proj_matrices: torch.Ten
     keep: list = []
     fe = [_dev_f32(f, dev) for f in features]
     ptrs = (C.c_void_p * V)(*[f.data_ptr() for f in fe])
-    proj = _host_f32(proj_matrices)
+    # homographies exactly as the reference builds them (fp32 on the host, TransMVSNet.py:77-81 + fmt/module.py:340-342):
+    # K[:3,:3] @ E[:3,:4] folded into E, then src . inverse(ref); rot = [:3,:3], trans = [:3,3]
+    pm = proj_matrices.detach().float().cpu()
+    ref_new = pm[:, 0, 0].clone()
+    ref_new[:, :3, :4] = torch.matmul(pm[:, 0, 1, :3, :3], pm[:, 0, 0, :3, :4])
+    ref_inv = torch.inverse(ref_new)
+    rt = torch.empty(N, V - 1, 12)
+    for i in range(1, V):
+        src_new = pm[:, i, 0].clone()
+        src_new[:, :3, :4] = torch.matmul(pm[:, i, 1, :3, :3], pm[:, i, 0, :3, :4])
+        T = torch.matmul(src_new, ref_inv)
+        rt[:, i - 1, :9] = T[:, :3, :3].reshape(N, 9)
+        rt[:, i - 1, 9:] = T[:, :3, 3]
+    proj = rt.contiguous()
     hyp = _dev_f32(depth_values, dev)
     sim = torch.empty(N, 1, D, h, w, dtype=torch.float32, device=dev)
     if view_weights is None:
@@ -64,7 +77,7 @@ def similarity_volume(features: Sequence[torch.Tensor], proj_matrices: torch.Ten
         vw_out = vw_in
         vw_in_ptr, pw_ref = vw_in.data_ptr(), None
     with torch.cuda.device(dev):
-        _lib.check(lib.ufo_costvolume_stage(ptrs, N, V, Cc, h, w, D, proj.data_ptr(), hyp.data_ptr(), vw_in_ptr, pw_ref,
+        _lib.check(lib.ufo_costvolume_stage_rt(ptrs, N, V, Cc, h, w, D, proj.data_ptr(), hyp.data_ptr(), vw_in_ptr, pw_ref,
                                             sim.data_ptr(), vw_out.data_ptr() if view_weights is None else None,
                                             _stream_ptr(dev)))
         torch.cuda.current_stream(dev).synchronize()

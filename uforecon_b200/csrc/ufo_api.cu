@@ -888,17 +888,40 @@ static int launch_costvol(const float* ref, const float* const* src_dev, const W
   return UFO_OK;
 }
 
-extern "C" int ufo_costvolume_stage(const float* const* feats, int32_t N, int32_t V, int32_t C, int32_t h, int32_t w, int32_t D,
-                                    const float* proj, const float* hyp, const float* vw_in, const UfoPixelwiseNet* pwn,
-                                    float* sim, float* vw_out, void* stream_) {
+static int costvolume_impl(const float* const* feats, int32_t N, int32_t V, int32_t C, int32_t h, int32_t w, int32_t D,
+                           const std::vector<WarpMats>& mats, const float* hyp, const float* vw_in, const UfoPixelwiseNet* pwn,
+                           float* sim, float* vw_out, cudaStream_t st);
+
+static int costvolume_check(const float* const* feats, int32_t N, int32_t V, int32_t C, int32_t D, const void* proj, const float* hyp,
+                            const float* vw_in, const UfoPixelwiseNet* pwn, float* sim, float* vw_out) {
   if (!feats || !proj || !hyp || !sim) return fail(UFO_EINVAL, "ufo_costvolume_stage: null argument");
   if (!vw_in && (!pwn || !vw_out)) return fail(UFO_EINVAL, "ufo_costvolume_stage: stage 1 needs the pixel-wise net and view_w_out");
   if (V < 2 || V > UFO_MAX_VIEWS || N < 1) return fail(UFO_EINVAL, "ufo_costvolume_stage: bad N/V");
   if (!((C == 32 && D == 48) || (C == 16 && D == 32) || (C == 8 && D == 8)))
     return fail(UFO_EINVAL, "ufo_costvolume_stage: unsupported (C=%d, D=%d); cascade is (32,48),(16,32),(8,8)", C, D);
-  if (int e = check_device()) return e;
-  cudaStream_t st = (cudaStream_t)stream_;
-  // warp matrices in double on the host
+  return check_device();
+}
+
+// Homographies supplied by the caller: rot_trans [N][V-1][12] = rows of rot (9) then trans (3) of src_proj_new . ref_proj_new^-1,
+// built by the host exactly as the reference builds them (fp32 torch.matmul / torch.inverse, TransMVSNet.py:77-81, module.py:340-342)
+extern "C" int ufo_costvolume_stage_rt(const float* const* feats, int32_t N, int32_t V, int32_t C, int32_t h, int32_t w, int32_t D,
+                                       const float* rot_trans, const float* hyp, const float* vw_in, const UfoPixelwiseNet* pwn,
+                                       float* sim, float* vw_out, void* stream_) {
+  if (int e = costvolume_check(feats, N, V, C, D, rot_trans, hyp, vw_in, pwn, sim, vw_out)) return e;
+  std::vector<WarpMats> mats((size_t)N * (V - 1));
+  for (size_t k = 0; k < mats.size(); ++k) {
+    memcpy(mats[k].r, rot_trans + k * 12, sizeof(float) * 9);
+    memcpy(mats[k].t, rot_trans + k * 12 + 9, sizeof(float) * 3);
+  }
+  return costvolume_impl(feats, N, V, C, h, w, D, mats, hyp, vw_in, pwn, sim, vw_out, (cudaStream_t)stream_);
+}
+
+// Homographies from the projection matrices, in double on the host (more accurate than the reference's fp32 inverse; use
+// ufo_costvolume_stage_rt for bit-level agreement with the reference's own matrices)
+extern "C" int ufo_costvolume_stage(const float* const* feats, int32_t N, int32_t V, int32_t C, int32_t h, int32_t w, int32_t D,
+                                    const float* proj, const float* hyp, const float* vw_in, const UfoPixelwiseNet* pwn,
+                                    float* sim, float* vw_out, void* stream_) {
+  if (int e = costvolume_check(feats, N, V, C, D, proj, hyp, vw_in, pwn, sim, vw_out)) return e;
   std::vector<WarpMats> mats((size_t)N * (V - 1));
   for (int n = 0; n < N; ++n) {
     double ref[16], ref_inv[16];
@@ -915,6 +938,12 @@ extern "C" int ufo_costvolume_stage(const float* const* feats, int32_t N, int32_
       }
     }
   }
+  return costvolume_impl(feats, N, V, C, h, w, D, mats, hyp, vw_in, pwn, sim, vw_out, (cudaStream_t)stream_);
+}
+
+static int costvolume_impl(const float* const* feats, int32_t N, int32_t V, int32_t C, int32_t h, int32_t w, int32_t D,
+                           const std::vector<WarpMats>& mats, const float* hyp, const float* vw_in, const UfoPixelwiseNet* pwn,
+                           float* sim, float* vw_out, cudaStream_t st) {
   PixelwiseDev pw{};
   if (!vw_in) {
     for (int c = 0; c < 16; ++c) {

@@ -59,9 +59,11 @@ __global__ void __launch_bounds__(256) k_costvol(const float* __restrict__ ref_c
   const float xf = (float)px, yf = (float)py;
   for (int i = 0; i < V - 1; ++i) {
     const WarpMats m = mats[n * (V - 1) + i];
-    const float rx = m.r[0] * xf + m.r[1] * yf + m.r[2];        // rot . [x, y, 1]
-    const float ry = m.r[3] * xf + m.r[4] * yf + m.r[5];
-    const float rz = m.r[6] * xf + m.r[7] * yf + m.r[8];
+    // rot . [x, y, 1] accumulated in k order with fused multiply-adds like the reference's sgemm (module.py:350); the
+    // depth scaling and the translation below are separate roundings like torch's elementwise ops (module.py:351-353)
+    const float rx = fmaf(m.r[2], 1.f, fmaf(m.r[1], yf, __fmul_rn(m.r[0], xf)));
+    const float ry = fmaf(m.r[5], 1.f, fmaf(m.r[4], yf, __fmul_rn(m.r[3], xf)));
+    const float rz = fmaf(m.r[8], 1.f, fmaf(m.r[7], yf, __fmul_rn(m.r[6], xf)));
     const float* src = src_cl[i] + (size_t)n * hw * C + 4 * l;
     float sim[PPL];
 #pragma unroll
@@ -73,12 +75,12 @@ __global__ void __launch_bounds__(256) k_costvol(const float* __restrict__ ref_c
       if (k >= D) break;                                        // uniform across the lane group
       // every lane of the group needs plane k's depth: broadcast from its owner lane kk
       const float d = __shfl_sync(gmask, dk[t], (threadIdx.x & 31) / LPP * LPP + kk);
-      const float X = rx * d + m.t[0], Y = ry * d + m.t[1], Z = rz * d + m.t[2];
+      const float X = __fadd_rn(__fmul_rn(rx, d), m.t[0]), Y = __fadd_rn(__fmul_rn(ry, d), m.t[1]), Z = __fadd_rn(__fmul_rn(rz, d), m.t[2]);
       float part = 0.f;
       if (!(Z < 1e-6f)) {                                       // invalid -> grid -99 -> zero sample
-        const float gx = (X / Z) / ((float)(w - 1) / 2.f) - 1.f;
-        const float gy = (Y / Z) / ((float)(h - 1) / 2.f) - 1.f;
-        const float ix = ((gx + 1.f) / 2.f) * (float)(w - 1), iy = ((gy + 1.f) / 2.f) * (float)(h - 1);
+        const float gx = __fsub_rn(__fdiv_rn(__fdiv_rn(X, Z), (float)(w - 1) / 2.f), 1.f);
+        const float gy = __fsub_rn(__fdiv_rn(__fdiv_rn(Y, Z), (float)(h - 1) / 2.f), 1.f);
+        const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.f), 2.f), (float)(w - 1)), iy = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.f), 2.f), (float)(h - 1));
         if ((ix > -1.f) && (ix < (float)w) && (iy > -1.f) && (iy < (float)h)) {
           const float fx = floorf(ix), fy = floorf(iy);
           const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;

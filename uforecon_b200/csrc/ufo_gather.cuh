@@ -110,8 +110,9 @@ __device__ __forceinline__ void tri_fetch(const float* __restrict__ vf, const fl
         const bool ok = (x >= 0) && (x < W) && (y >= 0) && (y < H) && (z >= 0) && (z < D);
         const float wgt = ok ? wx[dx] * wy[dy] * wz[dz] : 0.f;
         const size_t idx = ok ? ((size_t)z * H + y) * W + x : 0;
-        fa = fmaf(__ldg(vf + idx * kVolC + j), wgt, fa);
-        wa = fmaf(__ldg(vw + idx), wgt, wa);
+        // ATen's 3-D grid_sample (GridSampler.cpp, the non-vectorised CPU kernel) adds rounded products: no fused multiply-add
+        fa = __fadd_rn(fa, __fmul_rn(__ldg(vf + idx * kVolC + j), wgt));
+        wa = __fadd_rn(wa, __fmul_rn(__ldg(vw + idx), wgt));
       }
   f_out = fa;
   w_out = wa;
@@ -119,9 +120,12 @@ __device__ __forceinline__ void tri_fetch(const float* __restrict__ vf, const fl
 
 __device__ __forceinline__ void project_pt(const float* __restrict__ P, float x, float y, float z, float& u, float& v,
                                            float& qz) {
-  const float q0 = fmaf(P[0], x, fmaf(P[1], y, fmaf(P[2], z, P[3])));
-  const float q1 = fmaf(P[4], x, fmaf(P[5], y, fmaf(P[6], z, P[7])));
-  const float q2 = fmaf(P[8], x, fmaf(P[9], y, fmaf(P[10], z, P[11])));
+  // accumulated in k order with fused multiply-adds, like the sgemm behind the reference's torch.matmul(P, [x;1])
+  // (camera.py:387-388): at 1600 pixels one ulp of q moves u by 1e-4 pixel, so the order of the roundings decides
+  // whether the gathers agree with the reference to 1e-5 or to 1e-4
+  const float q0 = fmaf(P[3], 1.f, fmaf(P[2], z, fmaf(P[1], y, __fmul_rn(P[0], x))));
+  const float q1 = fmaf(P[7], 1.f, fmaf(P[6], z, fmaf(P[5], y, __fmul_rn(P[4], x))));
+  const float q2 = fmaf(P[11], 1.f, fmaf(P[10], z, fmaf(P[9], y, __fmul_rn(P[8], x))));
   u = q0 / q2;
   v = q1 / q2;
   qz = q2;
@@ -209,7 +213,7 @@ __device__ __forceinline__ void gather_point(const SceneDev& sc, float x, float 
         wl = (s == 0) ? ws : wl + ws;                                   // model.py:375-378
       }
 #pragma unroll
-      for (int s = 0; s < 3; ++s) G[s] = (n == 0) ? f[s] * wl : G[s] + f[s] * wl;  // model.py:381-386
+      for (int s = 0; s < 3; ++s) G[s] = (n == 0) ? __fmul_rn(f[s], wl) : __fadd_rn(G[s], __fmul_rn(f[s], wl));  // model.py:381-386
       Wsum = (n == 0) ? wl : Wsum + wl;
     }
 #pragma unroll
