@@ -96,6 +96,11 @@ def test_fullsize_fp32_sample_vs_oracle(full):
     print("fullsize fp32 kernel vs fp64 referee:", {a: f"{b:.1e}" for a, b in err64.items()})
     print("fullsize fp32 oracle vs fp64 referee:", {a: f"{b:.1e}" for a, b in orc64.items()})
     for a in ours:
+        # (1) directly against the reference's arithmetic, same bars as the small cases: the kernels mirror the order of
+        #     the reference's roundings in the projection / warps (sgemm k-order, unfused 3-D grid_sample), so no
+        #     resolution-dependent allowance is needed
+        assert err[a] <= base[a], (a, err[a])
+        # (2) and as close to the true value of the formulas as the reference itself is
         assert err64[a] <= 2 * orc64[a] + base[a], (a, err64[a], orc64[a])
     with torch.no_grad():
         rgb, depth, _, weight = orc.render(r["z"], r["radiance"], r["srdf"], sd["deviation_network.variance"])

@@ -142,6 +142,10 @@ static void pack_b(uint8_t* img, const float* W, int n_real, int k_real, int ldw
 // byte offsets of the k_view_tc2 weight image (mirrors tc::V2_W* in ufo_view_tc2.cuh, which only device TUs include)
 constexpr size_t kV2WQkv = 0, kV2WMrg = kV2WQkv + 240 * 80 * 2, kV2WMl0 = kV2WMrg + 80 * 96 * 2, kV2WMl2 = kV2WMl0 + 160 * 176 * 2,
                  kV2WRad = kV2WMl2 + 80 * 160 * 2, kV2WEnd = kV2WRad + 16 * 176 * 2;
+// byte offsets of the k_ray_tc2 weight pieces (mirrors tc::R2W_* in ufo_ray_tc2.cuh)
+constexpr size_t kR2WKv = 0, kR2WQ = kR2WKv + 176 * 96 * 2, kR2WMrg = kR2WQ + 96 * 96 * 2, kR2WMl0a = kR2WMrg + 96 * 96 * 2,
+                 kR2WMl0b = kR2WMl0a + 96 * 176 * 2, kR2WMl2 = kR2WMl0b + 80 * 176 * 2, kR2WDen = kR2WMl2 + 96 * 176 * 2,
+                 kR2WEnd = kR2WDen + 2 * 32 * 96 * 2;
 static int tc_weights_build(const UfoWeightsDesc* d, TcWeights* t, cudaStream_t st) {
   for (int f = 0; f < 2; ++f) {
     const bool bf16 = (f == 0);
@@ -212,6 +216,23 @@ static int tc_weights_build(const UfoWeightsDesc* d, TcWeights* t, cudaStream_t 
       pack_b(v2.data() + kV2WRad, rad.data(), 16, 176, 176, 16, 176, bf16);
       UFO_CUDA(cudaMalloc(&t->view_img2[f], v2.size()));
       UFO_CUDA(cudaMemcpyAsync(t->view_img2[f], v2.data(), v2.size(), cudaMemcpyHostToDevice, st));
+      UFO_CUDA(cudaStreamSynchronize(st));
+    }
+    {  // ray stage, two-CTAs-per-SM kernel (ufo_ray_tc2.cuh): seven streamed pieces
+      std::vector<uint8_t> r2(kR2WEnd, 0);
+      std::vector<float> kv((size_t)176 * 88);
+      memcpy(kv.data(), d->ray.k, sizeof(float) * 7744);
+      memcpy(kv.data() + 7744, d->ray.v, sizeof(float) * 7744);
+      pack_b(r2.data() + kR2WKv, kv.data(), 176, 88, 88, 176, 96, bf16);
+      pack_b(r2.data() + kR2WQ, d->ray.q, 88, 88, 88, 96, 96, bf16);
+      pack_b(r2.data() + kR2WMrg, d->ray.merge, 88, 88, 88, 96, 96, bf16);
+      pack_b(r2.data() + kR2WMl0a, d->ray.mlp0, 96, 176, 176, 96, 176, bf16);
+      pack_b(r2.data() + kR2WMl0b, d->ray.mlp0 + (size_t)96 * 176, 80, 176, 176, 80, 176, bf16);
+      pack_b(r2.data() + kR2WMl2, d->ray.mlp2, 88, 176, 176, 96, 176, bf16);
+      pack_b(r2.data() + kR2WDen, d->density.w0, 32, 88, 88, 32, 96, bf16, 0);
+      pack_b(r2.data() + kR2WDen + 32 * 96 * 2, d->density.w0, 32, 88, 88, 32, 96, bf16, 1);
+      UFO_CUDA(cudaMalloc(&t->ray_img2[f], r2.size()));
+      UFO_CUDA(cudaMemcpyAsync(t->ray_img2[f], r2.data(), r2.size(), cudaMemcpyHostToDevice, st));
       UFO_CUDA(cudaStreamSynchronize(st));
     }
     UFO_CUDA(cudaMalloc(&t->view_img[f], vi.size()));
@@ -345,7 +366,7 @@ extern "C" int ufo_weights_create(const UfoWeightsDesc* d, UfoWeights** out, voi
 
 extern "C" void ufo_weights_destroy(UfoWeights* w) {
   if (!w) return;
-  for (int f = 0; f < 2; ++f) { cudaFree(w->tc.view_img[f]); cudaFree(w->tc.ray_img[f]); cudaFree(w->tc.view_img2[f]); }
+  for (int f = 0; f < 2; ++f) { cudaFree(w->tc.view_img[f]); cudaFree(w->tc.ray_img[f]); cudaFree(w->tc.view_img2[f]); cudaFree(w->tc.ray_img2[f]); }
   cudaFree(w->blob);
   delete w;
 }

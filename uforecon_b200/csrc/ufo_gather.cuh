@@ -91,7 +91,12 @@ __device__ __forceinline__ float4 bil_fetch_rgbd(const float4* __restrict__ map,
 // matching single-channel weight volume [D][H][W].  (u,v,zn) in [-1,1] NDC.
 __device__ __forceinline__ void tri_fetch(const float* __restrict__ vf, const float* __restrict__ vw, int D, int H,
                                           int W, float u, float v, float zn, int j, float& f_out, float& w_out) {
-  const float ix = gs_unnorm<true>(u, W), iy = gs_unnorm<true>(v, H), iz = gs_unnorm<true>(zn, D);
+  // ATen's scalar 3-D kernel rounds the source index before it takes floor() and the tap weights; written with explicit
+  // roundings so that the compiler cannot fuse the last multiply into "ix - floor(ix)" (it did: vol24 was off by 2e-5 at
+  // 1600 pixels, where one ulp of ix is 1e-4 of a voxel)
+  const float ix = __fmul_rn(__fmul_rn(__fadd_rn(u, 1.f), 0.5f), (float)(W - 1));
+  const float iy = __fmul_rn(__fmul_rn(__fadd_rn(v, 1.f), 0.5f), (float)(H - 1));
+  const float iz = __fmul_rn(__fmul_rn(__fadd_rn(zn, 1.f), 0.5f), (float)(D - 1));
   f_out = 0.f;
   w_out = 0.f;
   const bool near_vol = (ix > -1.f) && (ix < (float)W) && (iy > -1.f) && (iy < (float)H) && (iz > -1.f) && (iz < (float)D);

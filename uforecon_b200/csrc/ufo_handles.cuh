@@ -15,6 +15,7 @@ struct TcWeights {
   uint8_t* view_img[2] = {nullptr, nullptr};   // [0] bf16, [1] fp16   (tc::V_WEND bytes)
   uint8_t* ray_img[2] = {nullptr, nullptr};    //                       (tc::RW_END bytes)
   uint8_t* view_img2[2] = {nullptr, nullptr};  // k_view_tc2 layout     (tc::V2_WEND bytes, ufo_view_tc2.cuh)
+  uint8_t* ray_img2[2] = {nullptr, nullptr};   // k_ray_tc2 pieces      (tc::R2W_END bytes, ufo_ray_tc2.cuh)
   ufo::ViewParams vp;
   ufo::RayParams rp;
 };

@@ -1,0 +1,513 @@
+// Ray stage, second generation: TWO CTAs PER SM.
+//
+//   LoFTREncoderLayer   code1/attention/transformer.py:35-58         (d = 88, tokens = the samples of one ray)
+//   LinearAttention     code1/attention/linear_attention.py:20-47
+//   order encoding      code1/ray_transformer.py:165-173,301-305
+//   DensityMLP          code1/ray_transformer.py:147-150,307
+//
+// k_ray_tc (ufo_xfmr_tc.cuh) is one 512-thread CTA per SM with 222 KB of shared memory, 14 lock-step phases per
+// 128-token tile; ncu showed 24 % of the issue slots used and the tensor pipe 15 % active - nothing runs while a CTA
+// waits for an MMA or a weight slot.  This kernel is built to be resident TWICE per SM (256 threads, <= 113 KB of shared
+// memory, 256 TMEM columns), so that the hardware interleaves two independent tiles:
+//   * every A operand an epilogue produces (x, Q', message, LayerNorm outputs, hidden layer, the split SRDF-head input)
+//     is written by its row owner into TMEM (tcgen05.st) and consumed by TS-form MMAs; shared memory holds only what must
+//     be there: the MN-major K'/V' tiles of the K^T.V product (later the block-diagonal KV operand) and the weights;
+//   * the 184 KB of weights stream through two 33 KB slots in seven pieces per tile (cp.async.bulk + mbarrier), each load
+//     issued as soon as the MMA that last read its slot has completed;
+//   * a thread owns one token row and one of two column halves.
+// TMEM columns (256): x [208,256) | k,v accumulator [0,176) | q accumulator [0,96) | Q' [96,144) | K^T.V per sequence
+// [0,96) [144,240) | message accumulator same | message operand [96,144) | merge accumulator [0,96) | [x | LN1] operand
+// [168,256) | mlp.0 accumulator, two passes [0,96) [0,80) | hidden operand [96,184) | mlp.2 accumulator [0,96) |
+// r_hi [96,144) r_lo [144,192) | SRDF-head accumulator [0,32).
+#pragma once
+#include "ufo_view_tc2.cuh"
+
+namespace ufo {
+namespace tc {
+// global image of the ray-stage weights for k_ray_tc2: seven pieces, each the exact shared-memory operand image
+constexpr uint32_t R2W_KV = 0;                             // [176][96]   rows: k 0..87 | v 88..175
+constexpr uint32_t R2W_Q = R2W_KV + 176 * 96 * 2;          // [96][96]    rows 88..95 zero
+constexpr uint32_t R2W_MRG = R2W_Q + 96 * 96 * 2;          // [96][96]
+constexpr uint32_t R2W_ML0A = R2W_MRG + 96 * 96 * 2;       // [96][176]   rows 0..95 of mlp.0
+constexpr uint32_t R2W_ML0B = R2W_ML0A + 96 * 176 * 2;     // [80][176]   rows 96..175
+constexpr uint32_t R2W_ML2 = R2W_ML0B + 80 * 176 * 2;      // [96][176]   rows 88..95 zero
+constexpr uint32_t R2W_DEN = R2W_ML2 + 96 * 176 * 2;       // [32][96] hi, [32][96] lo
+constexpr uint32_t R2W_END = R2W_DEN + 2 * 32 * 96 * 2;    // 178,688
+// shared-memory map (bytes)
+constexpr uint32_t R2_K = 0;                               // K' 11 chunks (MN-major B of the K^T.V product); later KV block-diagonal of sequence 0
+constexpr uint32_t R2_V = R2_K + 11 * kChunk;              // V' 12 chunks, chunk 11 = ones block; later sequence 1; the M = 128 read of the
+                                                           // K^T.V product runs 8 KB past it into slot 0 (finite weights, rows never used)
+constexpr uint32_t R2_SCR = R2_V + 96 * 96 * 2;            // LayerNorm / SRDF partials: inside the V' tile, behind the KV operand
+constexpr uint32_t R2_SLOT = R2_V + 12 * kChunk;           // two weight slots
+constexpr uint32_t R2_SLOT_BYTES = 176 * 96 * 2;           // 33,792: the largest piece
+constexpr uint32_t R2_BAR = R2_SLOT + 2 * R2_SLOT_BYTES;
+constexpr uint32_t R2_SMEM = R2_BAR + 64;
+static_assert(R2_SMEM <= 115712, "ray-stage (v2) shared memory: two CTAs must fit one SM");
+static_assert(R2_SCR + 2 * 128 * 8 <= R2_SLOT, "scratch overlaps the weight slots");
+}  // namespace tc
+
+// SN = 128: one ray per tile; SN = 64: two rays per tile.
+template <int SN, bool BF16>
+__global__ void __launch_bounds__(256, 2)
+k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams prm, const float* __restrict__ vout0,
+          const float* __restrict__ pe_table, const uint8_t* __restrict__ perm, long long P, float* __restrict__ srdf,
+          float* __restrict__ ray_out) {
+  using namespace tc;
+  constexpr uint32_t FMT = BF16 ? umma::kFmtBF16 : umma::kFmtF16;
+  constexpr int NSEQ = 128 / SN;
+  constexpr uint32_t C_X = 208, C_QP = 96, C_M = 96, C_XL = 168, C_H1 = 96, C_RHI = 96, C_RLO = 144;      // operands
+  constexpr uint32_t D_KV = 0, D_Q = 0, D_S0 = 0, D_S1 = 144, D_MRG = 0, D_ML0 = 0, D_ML2 = 0, D_DEN = 0;  // accumulators
+  extern __shared__ __align__(1024) uint8_t tc_smem[];
+  uint8_t* const smem = tc_smem;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + R2_BAR);          // MMA completion
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + R2_BAR + 8);     // [2] weight slot filled
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + R2_BAR + 32);
+  float2* red = reinterpret_cast<float2*>(smem + R2_SCR);
+  float* part_s = reinterpret_cast<float*>(smem + R2_SCR);
+  const int t = threadIdx.x, lane = t & 31, wl = t >> 5;
+  const int q = wl & 3, g = wl >> 2, r = q * 32 + lane;
+  const long long n_tiles = (P + 127) / 128;
+
+  if (wl == 0) umma::tmem_alloc(tmem_slot, 256);
+  if (t == 0) {
+    umma::mbar_init(bar, 1);
+    umma::mbar_init(full, 1);
+    umma::mbar_init(full + 1, 1);
+    umma::fence_barrier_init();
+  }
+  // the ones block of V' (rows 88..95 of the K^T.V product = sum_s K'_s) never changes
+  if (g == 0) {
+    float one[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+    st_chunk<BF16>(smem + R2_V, r, 11, one);
+  }
+  umma::fence_async_smem();
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tm = *tmem_slot;
+  const uint32_t tl = tm + ((uint32_t)(q * 32) << 16);
+  const uint32_t sm_base = umma::smem_u32(smem);
+  uint32_t ph = 0;
+
+  // ---- weight streaming: piece j of the running sequence goes to slot (pc & 1); all by thread 0
+  uint32_t pc_load = 0, pc_use = 0, fph0 = 0, fph1 = 0;
+  auto load_piece = [&](int j) {
+    const uint32_t off[7] = {R2W_KV, R2W_Q, R2W_MRG, R2W_ML0A, R2W_ML0B, R2W_ML2, R2W_DEN};
+    const uint32_t len[7] = {176 * 96 * 2, 96 * 96 * 2, 96 * 96 * 2, 96 * 176 * 2, 80 * 176 * 2, 96 * 176 * 2, 2 * 32 * 96 * 2};
+    const uint32_t s = pc_load & 1;
+    bulk_load(smem + R2_SLOT + s * R2_SLOT_BYTES, wimg + off[j], len[j], full + s);
+    ++pc_load;
+  };
+  // issuer: wait until the piece about to be used has landed; returns its slot's shared-memory address
+  auto use_piece = [&]() -> uint32_t {
+    const uint32_t s = pc_use & 1;
+    if (s == 0) { umma::mbar_wait(full, fph0); fph0 ^= 1; } else { umma::mbar_wait(full + 1, fph1); fph1 ^= 1; }
+    ++pc_use;
+    return sm_base + R2_SLOT + s * R2_SLOT_BYTES;
+  };
+  auto mma_wait = [&]() {
+    umma::mbar_wait(bar, ph);
+    ph ^= 1;
+    umma::tc_fence_after();
+  };
+  // TS-form K loop: A chunks from TMEM column a_col (8 columns per K step), B from a K-major weight tile with b_rows rows
+  auto issue_ts = [&](uint32_t d_col, uint32_t a_col, uint32_t b_addr, uint32_t b_rows, uint32_t n, int ksteps, uint32_t acc_first) {
+    const uint32_t idesc = umma::make_idesc(128, n, FMT, false, false);
+    const uint32_t lbo = b_rows * 16u;
+    for (int ks = 0; ks < ksteps; ++ks)
+      umma::mma_f16_ts(tm + d_col, tm + a_col + 8 * ks, umma::make_smem_desc(b_addr + 2 * ks * lbo, lbo, 128u), idesc, ks > 0 ? 1u : acc_first);
+  };
+
+  if (t == 0 && (long long)blockIdx.x < n_tiles) {
+    load_piece(0);
+    load_piece(1);
+  }
+  auto in_row_of = [&](long long tile) -> long long {
+    const long long prow = tile * 128 + r;
+    if (prow >= P) return -1;
+    return (SN == kNC) ? tc_slot(prow, 0) : tile * 128 + (perm ? (long long)perm[prow] : (long long)r);
+  };
+  // chunk c (8 channels) of this row's fp32 input: view-stage output (c < 10) or order encoding (c == 10)
+  auto x_chunk = [&](long long ir, int c, float4& a, float4& b) {
+    a = b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < 10) {
+      if (ir >= 0) {
+        a = __ldg(reinterpret_cast<const float4*>(vout0 + (size_t)ir * kDView + 8 * c));
+        b = __ldg(reinterpret_cast<const float4*>(vout0 + (size_t)ir * kDView + 8 * c + 4));
+      }
+    } else if (c == 10) {
+      a = __ldg(reinterpret_cast<const float4*>(pe_table + (r % SN) * 8));       // ray_transformer.py:301-303
+      b = __ldg(reinterpret_cast<const float4*>(pe_table + (r % SN) * 8 + 4));
+    }
+  };
+  // chunks [c0, c1) of the 16-bit x operand -> TMEM columns col0 + 4 c
+  auto x_stage = [&](long long ir, int c0, int c1, uint32_t col0) {
+#pragma unroll
+    for (int c = c0; c < c1; ++c) {
+      float4 a, b;
+      x_chunk(ir, c, a, b);
+      umma::tmem_st4(tl + col0 + 4 * c, umma::pack2<BF16>(a.x, a.y), umma::pack2<BF16>(a.z, a.w), umma::pack2<BF16>(b.x, b.y),
+                     umma::pack2<BF16>(b.z, b.w));
+    }
+  };
+
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long prow = tile * 128 + r;           // this thread's token: ray prow / SN, sorted sample prow % SN
+    const bool row_ok = prow < P;
+    const long long in_row = in_row_of(tile);
+    const bool has_next = tile + (long long)gridDim.x < n_tiles;
+    // ---- R0: x = [view-stage token 0 output | order encoding | 0] -> 16-bit A operand in TMEM (chunks 6 g .. 6 g + 5)
+    if (g == 0) x_stage(in_row, 0, 6, C_X); else x_stage(in_row, 6, 12, C_X);
+    umma::tmem_st_wait();
+    umma::tc_fence_before();
+    __syncthreads();
+    // ---- R1a: k | v = x . Wkv^T
+    if (t == 0) {
+      const uint32_t b = use_piece();
+      umma::tc_fence_after();
+      issue_ts(D_KV, C_X, b, 176, 176, 6, 0);
+      umma::commit(bar);
+    }
+    mma_wait();
+    if (t == 0) load_piece(2);                                   // merge weights -> the slot Wkv leaves
+    // ---- R1b: q = x . Wq^T, issued now so that it runs under the k/v epilogue (its accumulator aliases k: see below)
+    // ---- R2a: K' = elu(k)+1, V' = v -> MN-major operand tiles in shared memory   (linear_attention.py:36-41)
+    {
+      auto r2a = [&](auto GGc) {
+        constexpr int GG = decltype(GGc)::value;
+        constexpr int C0 = GG ? 6 : 0, NC = GG ? 5 : 6;          // chunks of this column half: 0..5 | 6..10
+        float2 kk[NC][4], vv[NC][4];
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+          tmem_ld8p(tl + D_KV + 8 * (C0 + i), kk[i]);
+          tmem_ld8p(tl + D_KV + 88 + 8 * (C0 + i), vv[i]);
+        }
+        umma::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) kk[i][k] = elu1_2(kk[i][k]);
+          st_chunk2<BF16>(smem + R2_K, r, C0 + i, kk[i]);
+          st_chunk2<BF16>(smem + R2_V, r, C0 + i, vv[i]);
+        }
+      };
+      UFO_G2_DISPATCH(r2a)
+    }
+    umma::fence_async_smem();
+    umma::tc_fence_before();
+    __syncthreads();
+    // ---- R1b: q = x . Wq^T   (the k | v accumulator is consumed)
+    if (t == 0) {
+      const uint32_t b = use_piece();
+      umma::tc_fence_after();
+      issue_ts(D_Q, C_X, b, 96, 96, 6, 0);
+      umma::commit(bar);
+    }
+    mma_wait();
+    if (t == 0) load_piece(3);                                   // mlp.0 rows 0..95
+    // ---- R2b: Q' = elu(q)+1 -> A operand of the message GEMM (chunk 11 = 0)
+    {
+      auto r2b = [&](auto GGc) {
+        constexpr int GG = decltype(GGc)::value;
+        constexpr int C0 = GG ? 6 : 0, NC = GG ? 5 : 6;
+        float2 a[NC][4];
+#pragma unroll
+        for (int i = 0; i < NC; ++i) tmem_ld8p(tl + D_Q + 8 * (C0 + i), a[i]);
+        umma::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) a[i][k] = elu1_2(a[i][k]);
+          umma::tmem_st4(tl + C_QP + 4 * (C0 + i), pack2v<BF16>(a[i][0]), pack2v<BF16>(a[i][1]), pack2v<BF16>(a[i][2]), pack2v<BF16>(a[i][3]));
+        }
+        if (GG == 1) umma::tmem_st4(tl + C_QP + 44, 0u, 0u, 0u, 0u);
+        umma::tmem_st_wait();
+      };
+      UFO_G2_DISPATCH(r2b)
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    // ---- R3: per sequence  D[b][a] = sum_s V'[s][b] K'[s][a]   (rows 88..95 = sum_s K'[s][a]);  both operands MN-major
+    if (t == 0) {
+      umma::tc_fence_after();
+      const uint32_t idesc = umma::make_idesc(128, 96, FMT, true, true);
+#pragma unroll
+      for (int sq = 0; sq < NSEQ; ++sq) {
+        for (int ks = 0; ks < SN / 16; ++ks) {
+          const uint32_t off = (uint32_t)(sq * (SN / 16) + ks) * 256u;
+          const uint64_t ad = umma::make_smem_desc(sm_base + R2_V + off, 128, kChunk);
+          const uint64_t bd = umma::make_smem_desc(sm_base + R2_K + off, 128, kChunk);
+          umma::mma_f16(tm + (sq == 0 ? D_S0 : D_S1), ad, bd, idesc, ks > 0);
+        }
+      }
+      umma::commit(bar);
+    }
+    mma_wait();
+    // ---- R4: block-diagonal KV (per head 11x11) + per-head K-sum rows as the B operand of the message GEMM
+    if (r < 96) {
+      const int hr = r < 88 ? r / 11 : r - 88;       // rows 0..87: KV_h of the row's head; row 88+h: the K-sum of head h
+      auto r4 = [&](auto GGc) {
+        constexpr int GG = decltype(GGc)::value;
+#pragma unroll
+        for (int sq = 0; sq < NSEQ; ++sq) {
+          uint8_t* kvbd = smem + (sq == 0 ? R2_K : R2_V);        // [96 rows b][96 cols a], chunk stride 96*16
+          float v[6][8];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) umma::tmem_ld8(tl + (sq == 0 ? D_S0 : D_S1) + 8 * (6 * GG + i), v[i]);
+          umma::tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            const int c = 6 * GG + i;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[i][k] = ((8 * c + k) < 88 && ((8 * c + k) / 11) == hr) ? v[i][k] : 0.f;
+            *reinterpret_cast<uint4*>(kvbd + c * (96 * 16) + r * 16) = pack8<BF16>(v[i]);
+          }
+        }
+      };
+      UFO_G2_DISPATCH(r4)
+    }
+    umma::fence_async_smem();
+    umma::tc_fence_before();
+    __syncthreads();
+    // ---- R5: message numerator Q'.KV_h (columns 0..87) and per-head normalisers Q'_h.Ksum_h (columns 88..95)
+    if (t == 0) {
+      umma::tc_fence_after();
+#pragma unroll
+      for (int sq = 0; sq < NSEQ; ++sq) issue_ts(sq == 0 ? D_S0 : D_S1, C_QP, sm_base + (sq == 0 ? R2_K : R2_V), 96, 96, 6, 0);
+      umma::commit(bar);
+    }
+    mma_wait();
+    // ---- R6: msg = numerator / (normaliser + 1e-6)                (linear_attention.py:44-45) -> A operand of the merge
+    {
+      const uint32_t dm = tl + ((NSEQ == 1 || r < SN) ? D_S0 : D_S1);
+      float zr[8];
+      umma::tmem_ld8(dm + 88, zr);
+      auto r6 = [&](auto GGc) {
+        constexpr int GG = decltype(GGc)::value;
+        constexpr int C0 = GG ? 6 : 0, NC = GG ? 5 : 6;
+        float v[NC][8];
+#pragma unroll
+        for (int i = 0; i < NC; ++i) umma::tmem_ld8(dm + 8 * (C0 + i), v[i]);
+        umma::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) zr[j] = 1.f / (zr[j] + 1e-6f);
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+          const int c = C0 + i;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[i][k] *= zr[(8 * c + k) / 11];      // static index: head of column 8c+k
+          const uint4 u = pack8<BF16>(v[i]);
+          umma::tmem_st4(tl + C_M + 4 * c, u.x, u.y, u.z, u.w);
+        }
+        if (GG == 1) umma::tmem_st4(tl + C_M + 44, 0u, 0u, 0u, 0u);
+        umma::tmem_st_wait();
+      };
+      UFO_G2_DISPATCH(r6)
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    // ---- R7: merge
+    if (t == 0) {
+      const uint32_t b = use_piece();
+      umma::tc_fence_after();
+      issue_ts(D_MRG, C_M, b, 96, 96, 6, 0);
+      umma::commit(bar);
+    }
+    mma_wait();
+    if (t == 0) load_piece(4);                                   // mlp.0 rows 96..175
+    // ---- R8: LayerNorm 1 -> second half of the concat operand [x | LN1] (chunks 11..21); x re-staged as chunks 0..10
+    {
+      auto r8 = [&](auto GGc) {
+        constexpr int GG = decltype(GGc)::value;
+        constexpr int C0 = GG ? 6 : 0, NC = GG ? 5 : 6;
+        float2 v[NC][4];
+#pragma unroll
+        for (int i = 0; i < NC; ++i) tmem_ld8p(tl + D_MRG + 8 * (C0 + i), v[i]);
+        umma::tmem_ld_wait();
+        float2 s = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < NC; ++i)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            s = __fadd2_rn(s, v[i][k]);
+            q2 = __ffma2_rn(v[i][k], v[i][k], q2);
+          }
+        red[GG * 128 + r] = make_float2(s.x + s.y, q2.x + q2.y);
+        if (GG == 0) x_stage(in_row, 0, 6, C_XL); else x_stage(in_row, 6, 11, C_XL);      // under the barrier
+        umma::tc_fence_before();
+        __syncthreads();
+        const float2 st = ln2_stats(red, r, 1.f / 88.f);
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+          const int c = C0 + i;
+          float2 o[4];
+          ln_apply(v[i], st, prm.n1w + 8 * c, prm.n1b + 8 * c, o);
+          umma::tmem_st4(tl + C_XL + 4 * (11 + c), pack2v<BF16>(o[0]), pack2v<BF16>(o[1]), pack2v<BF16>(o[2]), pack2v<BF16>(o[3]));
+        }
+        umma::tmem_st_wait();
+      };
+      UFO_G2_DISPATCH(r8)
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    // ---- R9a: mlp.0 on [x | LN1]  (K = 176), output rows 0..95
+    if (t == 0) {
+      const uint32_t b = use_piece();
+      umma::tc_fence_after();
+      issue_ts(D_ML0, C_XL, b, 96, 96, 11, 0);
+      umma::commit(bar);
+    }
+    mma_wait();
+    if (t == 0) load_piece(5);                                   // mlp.2
+    // ---- R10a: ReLU -> hidden operand chunks 0..11
+    {
+      auto r10a = [&](auto GGc) {
+        constexpr int GG = decltype(GGc)::value;
+        float2 v[6][4];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) tmem_ld8p(tl + D_ML0 + 8 * (6 * GG + i), v[i]);
+        umma::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+          umma::tmem_st4(tl + C_H1 + 4 * (6 * GG + i), relu_pack2<BF16>(v[i][0]), relu_pack2<BF16>(v[i][1]), relu_pack2<BF16>(v[i][2]),
+                         relu_pack2<BF16>(v[i][3]));
+        umma::tmem_st_wait();
+      };
+      UFO_G2_DISPATCH(r10a)
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    // ---- R9b: mlp.0 output rows 96..175 (the first accumulator is consumed)
+    if (t == 0) {
+      const uint32_t b = use_piece();
+      umma::tc_fence_after();
+      issue_ts(D_ML0, C_XL, b, 80, 80, 11, 0);
+      umma::commit(bar);
+    }
+    mma_wait();
+    if (t == 0) load_piece(6);                                   // SRDF head layer 0 (hi | lo)
+    // ---- R10b: ReLU -> hidden operand chunks 12..21 (over the dead [x | LN1] operand)
+    {
+      auto r10b = [&](auto GGc) {
+        constexpr int GG = decltype(GGc)::value;
+        float2 v[5][4];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) tmem_ld8p(tl + D_ML0 + 8 * (5 * GG + i), v[i]);
+        umma::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+          umma::tmem_st4(tl + C_H1 + 4 * (12 + 5 * GG + i), relu_pack2<BF16>(v[i][0]), relu_pack2<BF16>(v[i][1]), relu_pack2<BF16>(v[i][2]),
+                         relu_pack2<BF16>(v[i][3]));
+        umma::tmem_st_wait();
+      };
+      UFO_G2_DISPATCH(r10b)
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    // ---- R11: mlp.2
+    if (t == 0) {
+      const uint32_t b = use_piece();
+      umma::tc_fence_after();
+      issue_ts(D_ML2, C_H1, b, 96, 96, 11, 0);
+      umma::commit(bar);
+    }
+    mma_wait();
+    if (t == 0 && has_next) load_piece(0);                       // the next tile's Wkv
+    // ---- R12: LayerNorm 2, residual in fp32 from the fp32 input, split hi/lo for the SRDF head
+    {
+      auto r12 = [&](auto GGc) {
+        constexpr int GG = decltype(GGc)::value;
+        constexpr int C0 = GG ? 6 : 0, NC = GG ? 5 : 6;
+        float2 v[NC][4];
+#pragma unroll
+        for (int i = 0; i < NC; ++i) tmem_ld8p(tl + D_ML2 + 8 * (C0 + i), v[i]);
+        umma::tmem_ld_wait();
+        float2 s = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < NC; ++i)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            s = __fadd2_rn(s, v[i][k]);
+            q2 = __ffma2_rn(v[i][k], v[i][k], q2);
+          }
+        red[GG * 128 + r] = make_float2(s.x + s.y, q2.x + q2.y);
+        umma::tc_fence_before();
+        __syncthreads();
+        const float2 st = ln2_stats(red, r, 1.f / 88.f);
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+          const int c = C0 + i;
+          float4 xa, xb;
+          x_chunk(in_row, c, xa, xb);                            // fp32 residual input of this row
+          float2 o2[4];
+          ln_apply(v[i], st, prm.n2w + 8 * c, prm.n2b + 8 * c, o2);
+          const float o[8] = {xa.x + o2[0].x, xa.y + o2[0].y, xa.z + o2[1].x, xa.w + o2[1].y,
+                              xb.x + o2[2].x, xb.y + o2[2].y, xb.z + o2[3].x, xb.w + o2[3].y};
+          float hi[8], lo[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) split_hi_lo<BF16>(o[k], hi[k], lo[k]);
+          if (ray_out != nullptr && row_ok) {
+            float4* dst = reinterpret_cast<float4*>(ray_out + (size_t)prow * kDRay + 8 * c);
+            dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+            dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+          }
+          const uint4 uh = pack8<BF16>(hi), ul = pack8<BF16>(lo);
+          umma::tmem_st4(tl + C_RHI + 4 * c, uh.x, uh.y, uh.z, uh.w);
+          umma::tmem_st4(tl + C_RLO + 4 * c, ul.x, ul.y, ul.z, ul.w);
+        }
+        if (GG == 1) {
+          umma::tmem_st4(tl + C_RHI + 44, 0u, 0u, 0u, 0u);
+          umma::tmem_st4(tl + C_RLO + 44, 0u, 0u, 0u, 0u);
+        }
+        umma::tmem_st_wait();
+      };
+      UFO_G2_DISPATCH(r12)
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    // ---- R13: DensityMLP layer 0 in split precision: r_hi.W_hi + r_lo.W_hi + r_hi.W_lo   (ray_transformer.py:147-150)
+    if (t == 0) {
+      const uint32_t b = use_piece();
+      umma::tc_fence_after();
+      issue_ts(D_DEN, C_RHI, b, 32, 32, 6, 0);
+      issue_ts(D_DEN, C_RLO, b, 32, 32, 6, 1);
+      issue_ts(D_DEN, C_RHI, b + 32 * 96 * 2, 32, 32, 6, 1);
+      umma::commit(bar);
+    }
+    mma_wait();
+    if (t == 0 && has_next) load_piece(1);                       // the next tile's Wq
+    // ---- R14: DensityMLP tail 32 -> 16 -> 1 in fp32 (hidden units 8 g .. 8 g + 7 per thread)
+    {
+      float h[32];
+      umma::tmem_ld16(tl + D_DEN, h);
+      umma::tmem_ld16(tl + D_DEN + 16, h + 16);
+      umma::tmem_ld_wait();
+      auto tail = [&](auto GGc) {
+        constexpr int GG = decltype(GGc)::value;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) h[i] = fmaxf(h[i] + prm.db0[i], 0.f);
+        float part = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int o = 8 * GG + j;
+          float2 acc = make_float2(prm.db2[o], 0.f);
+#pragma unroll
+          for (int i = 0; i < 32; i += 2)
+            acc = __ffma2_rn(make_float2(h[i], h[i + 1]), make_float2(prm.dw2[o][i], prm.dw2[o][i + 1]), acc);
+          part = fmaf(fmaxf(acc.x + acc.y, 0.f), prm.dw4[o], part);
+        }
+        part_s[GG * 128 + r] = part;
+      };
+      UFO_G2_DISPATCH(tail)
+      umma::tc_fence_before();
+      __syncthreads();
+      if (g == 0 && row_ok) srdf[prow] = prm.db4 + (part_s[r] + part_s[128 + r]);
+    }
+    // the scratch is rewritten by the next tile's R2a only after its R0 barrier; TMEM is rewritten after that barrier too
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (wl == 0) umma::tmem_dealloc(tm, 256);
+}
+
+}  // namespace ufo

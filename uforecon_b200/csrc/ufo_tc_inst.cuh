@@ -4,6 +4,7 @@
 #include "ufo_handles.cuh"
 #include "ufo_xfmr_tc.cuh"
 #include "ufo_view_tc2.cuh"
+#include "ufo_ray_tc2.cuh"
 #include <cstdlib>
 
 namespace ufo {
@@ -39,16 +40,27 @@ static int launch_tc_pass(const UfoScene* sc, const UfoWeights* w, int R, int ha
     UFO_KERNEL("k_view_tc", st, k_view_tc<NV, BF16><<<grid, tc::kThreads, tc::V_SMEM, st>>>(w->tc.view_img[f], w->tc.vp, ws.tok, ws.rgbm, ws.dirs, (int)P, half,
                                                                                            ws.vout0, ws.radiance));
   }
-  if (half == 0) {
-    const long long tiles = (P + 127) / 128;
-    const int grid = (int)(tiles < sms ? tiles : sms);
+  static const int ray_gen = getenv("UFO_RAY_KERNEL") ? atoi(getenv("UFO_RAY_KERNEL")) : 2;
+  static_assert(tc::R2W_END == 178688, "k_ray_tc2 weight image size (mirrored in ufo_api.cu)");
+  const long long PR = half == 0 ? P : (long long)R * kNS;           // tokens of the ray stage: 64 or all 128 per ray
+  const long long rtiles = (PR + 127) / 128;
+  if (ray_gen == 2) {      // two CTAs per SM (ufo_ray_tc2.cuh)
+    const int grid = (int)(rtiles < 2 * sms ? rtiles : 2 * sms);
+    if (half == 0) {
+      UFO_SMEM_ATTR((k_ray_tc2<kNC, BF16>), (int)tc::R2_SMEM);
+      UFO_KERNEL("k_ray_tc", st, k_ray_tc2<kNC, BF16><<<grid, 256, tc::R2_SMEM, st>>>(w->tc.ray_img2[f], w->tc.rp, ws.vout0, w->pe_table, nullptr, PR, ws.srdf, ray_out_tap));
+    } else {
+      UFO_SMEM_ATTR((k_ray_tc2<kNS, BF16>), (int)tc::R2_SMEM);
+      UFO_KERNEL("k_ray_tc", st, k_ray_tc2<kNS, BF16><<<grid, 256, tc::R2_SMEM, st>>>(w->tc.ray_img2[f], w->tc.rp, ws.vout0, w->pe_table, ws.perm, PR, ws.srdf, ray_out_tap));
+    }
+  } else if (half == 0) {
+    const int grid = (int)(rtiles < sms ? rtiles : sms);
     UFO_SMEM_ATTR((k_ray_tc<kNC, BF16>), (int)tc::R_SMEM);
-    UFO_KERNEL("k_ray_tc", st, k_ray_tc<kNC, BF16><<<grid, tc::kThreads, tc::R_SMEM, st>>>(w->tc.ray_img[f], w->tc.rp, ws.vout0, w->pe_table, nullptr, P, ws.srdf, ray_out_tap));
+    UFO_KERNEL("k_ray_tc", st, k_ray_tc<kNC, BF16><<<grid, tc::kThreads, tc::R_SMEM, st>>>(w->tc.ray_img[f], w->tc.rp, ws.vout0, w->pe_table, nullptr, PR, ws.srdf, ray_out_tap));
   } else {
-    const long long tiles = R;
-    const int grid = (int)(tiles < sms ? tiles : sms);
+    const int grid = (int)(rtiles < sms ? rtiles : sms);
     UFO_SMEM_ATTR((k_ray_tc<kNS, BF16>), (int)tc::R_SMEM);
-    UFO_KERNEL("k_ray_tc", st, k_ray_tc<kNS, BF16><<<grid, tc::kThreads, tc::R_SMEM, st>>>(w->tc.ray_img[f], w->tc.rp, ws.vout0, w->pe_table, ws.perm, (long long)R * kNS, ws.srdf, ray_out_tap));
+    UFO_KERNEL("k_ray_tc", st, k_ray_tc<kNS, BF16><<<grid, tc::kThreads, tc::R_SMEM, st>>>(w->tc.ray_img[f], w->tc.rp, ws.vout0, w->pe_table, ws.perm, PR, ws.srdf, ray_out_tap));
   }
   return UFO_OK;
 }
