@@ -123,7 +123,9 @@ def load_model(nv: int, state_dict: dict, device="cpu"):
     warnings.filterwarnings("ignore")
     from code1.model import UFORecon          # the reference, unmodified
     torch.manual_seed(0)
-    m = UFORecon(canonical_args(n_view=nv)).eval()
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):     # the reference's constructors print banners; stdout carries bench.py's JSON line
+        m = UFORecon(canonical_args(n_view=nv)).eval()
     missing, unexpected = m.load_state_dict(state_dict, strict=False)
     assert not unexpected, unexpected
     hot = [k for k in missing if k.startswith("ray_transformer") or k.startswith("deviation")]

@@ -16,9 +16,9 @@ views, unfavourable set 1/16/36, 64+64 samples per ray) rendered by ``ufo_render
 * ``roofline``      the dominant kernel of the timed region against its roofline.
 * ``cpu_baseline``  the CPU restatement of the reference (oracle/) timed on this box's host cores on a bounded
                     sample of the same workload (N=1 only).
-* N>1: weak scaling - every rank renders its own full depth map (BASELINE configs[4]: image-sharded sweep);
-  ``sec_per_depth_map_sharded`` additionally times ONE depth map with its rows sharded over the N ranks
-  (configs[2]) including the gather of depth/rgb to rank 0.
+* N>1: STRONG scaling is the headline - one depth map per step (BASELINE configs[2]: favourable view set), contiguous row
+  blocks of the ray grid per rank, the NCCL gather of depth/rgb to rank 0 inside the timed region; ``weak_scaling`` (one full
+  map per rank, no communication) is an extra.  ``--sweep 49`` runs BASELINE configs[4] (images round-robin over the ranks).
 
 ``--impl reference`` times the reference's own CPU implementation of the same path on the host cores - the UNMODIFIED
 reference staged under baseline/_ref by ``baseline/reference_arm.py`` (the oracle port only if that copy is absent) - and
@@ -263,14 +263,18 @@ def run_reference(args):
 
 
 def workload_config(args, views, ckpt_src, mode_name):
+    n = max(args.gpus, 1)
+    cfg = "BASELINE configs[1]" if n == 1 else "BASELINE configs[2]: rays sharded over the GPUs"
+    par = ("1 GPU, one full depth map per step" if n == 1 else
+           f"{n} GPUs, ONE depth map per step: contiguous row blocks of the ray grid per rank (no collective in the render), "
+           f"one NCCL gather of depth/rgb to rank 0 inside the timed region")
     return {"workload": f"DTU-shaped {args.width}x{args.height} ray grid, {args.nv} source views {views} "
-                        f"({args.views}), 64 coarse + 64 importance samples/ray, full depth-map render "
-                        f"(BASELINE configs[1])",
+                        f"({args.views}), 64 coarse + 64 importance samples/ray, full depth-map render ({cfg})",
             "rays_per_depth_map": args.width * args.height, "n_views": args.nv, "mode": mode_name,
             "checkpoint": ckpt_src,
             "l2": "inputs larger than L2 (scene tensors 4.2 GB at 1600x1216 vs 126 MB L2); no explicit flush",
             "timing": "value/ms_per_step: K steps between CUDA events, no per-kernel brackets; roofline: the same K steps repeated with every launch bracketed by CUDA events",
-            "parallelism": f"dp{args.gpus} (one full depth map per rank per step; no collective in the timed region)"}
+            "parallelism": par}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -343,12 +347,24 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    begin, n_mine = ufodist.shard_rows(H, W, world, rank)
+    counts = ufodist.shard_counts(H, W, world)
+    if args.rays > 0:
+        begin, n_mine, counts = 0, n_rays, [n_rays] * world
+
+    def step_sharded():
+        """one depth map over all ranks: this rank's row block, then the gather of depth/rgb to rank 0"""
+        step_resident(begin, n_mine)
+        return ufodist.gather_depth_rgb(out_depthz[:n_mine], out_rgb[:n_mine], counts) if world > 1 else None
+
+    step_main = step_resident if world == 1 else step_sharded
     # ---- warm-up
     for _ in range(args.warmup):
-        step_resident()
+        step_main()
     barrier()
 
-    # ---- timed region: K steps, CUDA events on the launching stream
+    # ---- timed region: K steps, CUDA events on the launching stream.  N = 1: one full depth map per step.  N > 1: ONE
+    #      depth map per step, rows sharded over the ranks, gather to rank 0 included (strong scaling)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -357,38 +373,51 @@ def run_b200(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
-        step_resident()
+        step_main()
     e1.record(stream)
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = lib.ufo_launch_count() - launches0
     ms_step = ms_total / args.steps
-    value = world * n_rays * args.steps / (ms_total * 1e-3)
+    value = n_rays * args.steps / (ms_total * 1e-3)
     # ---- the same K steps again with every launch bracketed by CUDA events (ufo_profile_*): per-kernel device time
     #      for the roofline entries; kept out of the region above because the 2 event records per launch cost ~3 %
     _lib.profile_begin()
     barrier()
     e0.record(stream)
     for _ in range(args.steps):
-        step_resident()
+        step_main()
     e1.record(stream)
     barrier()
     ms_prof_total = max_over_ranks(e0.elapsed_time(e1))
     prof = _lib.profile_end(256)
     clk = clocks.stop() if rank == 0 else None
 
-    # ---- e2e: host buffers, copies inside the timed region
-    for _ in range(1):
-        step_e2e()
+    # ---- e2e: host buffers, copies inside the timed region.  N = 1: ufo_render_rays_host.  N > 1: every rank uploads the
+    #      uniforms of its row block from pinned host memory, renders, the blocks are gathered to rank 0 and rank 0 copies the
+    #      assembled depth map to pinned host memory
+    def step_e2e_sharded():
+        u_c[:, begin:begin + n_mine].copy_(u_c_host[:, begin:begin + n_mine], non_blocking=True)
+        u_f[:, begin:begin + n_mine].copy_(u_f_host[:, begin:begin + n_mine], non_blocking=True)
+        got = step_sharded()
+        if rank == 0:
+            depth_host.copy_(got[0], non_blocking=True)
+            rgb_host.copy_(got[1], non_blocking=True)
+            stream.synchronize()
+
+    step_e2e_main = step_e2e if world == 1 else step_e2e_sharded
+    step_e2e_main()
     barrier()
     k_e2e = max(1, min(args.steps, args.e2e_steps))
     e0.record(stream)
     for _ in range(k_e2e):
-        step_e2e()
+        step_e2e_main()
     e1.record(stream)
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
-    e2e_value = world * n_rays * k_e2e / (ms_e2e * 1e-3)
+    e2e_value = n_rays * k_e2e / (ms_e2e * 1e-3)
+    e2e_h2d = 2 * 64 * 4 * n_rays if world == 1 else 2 * 64 * 4 * n_rays    # all ranks together upload the whole map's uniforms
+    e2e_d2h = 16 * n_rays
 
     # ---- accuracy of this mode at THIS workload (outside every timed region): a band of rows rendered in the measured
     #      mode and in fp32 mode (the 1e-5 parity path) with the same uniforms -> the north-star tolerance figures
@@ -399,25 +428,23 @@ def run_b200(args):
         except Exception as ex:  # reported extra: never fail the headline line
             accuracy = {"error": str(ex)}
 
-    # ---- strong-scaling extra: ONE depth map with rows sharded over the ranks (+ gather to rank 0)
-    sharded_s = None
-    begin, n_mine = ufodist.shard_rows(H, W, world, rank)
-    counts = ufodist.shard_counts(H, W, world)
-    if args.rays > 0:
-        begin, n_mine, counts = 0, n_rays, [n_rays] * world
-    for it in range(3):
+    # ---- weak-scaling extra (N > 1): every rank renders its own full depth map, no communication
+    weak = None
+    if world > 1:
+        step_resident()
         barrier()
         e0.record(stream)
-        step_resident(begin, n_mine)
-        got = ufodist.gather_depth_rgb(out_depthz[:n_mine], out_rgb[:n_mine], counts) if world > 1 else None
+        for _ in range(2):
+            step_resident()
         e1.record(stream)
         barrier()
-        sharded_s = max_over_ranks(e0.elapsed_time(e1)) * 1e-3
-    del got
+        ms_w = max_over_ranks(e0.elapsed_time(e1))
+        weak = {"value": world * n_rays * 2 / (ms_w * 1e-3), "unit": UNIT, "ms_per_step": ms_w / 2,
+                "what": "one full depth map per rank per step, no collective (image-sharded sweeps, BASELINE configs[4])"}
 
     # ---- roofline of the dominant kernel
     pk = peaks()
-    roofs = roofline_entries(prof, args, n_rays, pk)
+    roofs = roofline_entries(prof, args, n_rays if world == 1 else n_mine, pk)
     roof = roofs[0] if roofs else None
     costvol = None
     if rank == 0 and world == 1 and not args.no_costvolume:
@@ -450,24 +477,34 @@ def run_b200(args):
         except Exception as ex:  # reported extra: never fail the headline line
             ref_cuda = {"error": repr(ex)}
 
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        try:
+            extras = bench_extras(batch, scene, sd, dev, mode)
+        except Exception as ex:  # reported extra: never fail the headline line
+            extras = {"error": repr(ex)}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
             "dtype": {"fp32": "f32", "tc16": "f16"}[args.mode], "data": "synthetic",
             "sec_per_depth_map": ms_step * 1e-3,
-            "sec_per_depth_map_sharded": sharded_s,
-            "config": workload_config(args, views, ckpt_src, args.mode),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * 64 * 4 * n_rays,
-                    "d2h_bytes_per_step": 16 * n_rays, "steps": k_e2e,
-                    "api": "ufo_render_rays_host (pinned host uniforms in, pinned host depth/rgb out)"},
+            "config": dict(workload_config(args, views, ckpt_src, args.mode), accuracy=accuracy,
+                           rays_per_rank=[int(c) for c in counts] if world > 1 else [int(n_rays)]),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_h2d,
+                    "d2h_bytes_per_step": e2e_d2h, "steps": k_e2e,
+                    "api": ("ufo_render_rays_host (pinned host uniforms in, pinned host depth/rgb out)" if world == 1 else
+                            "per rank: pinned host uniforms of its row block in, ufo_render_rays, NCCL gather to rank 0, assembled depth/rgb to pinned host")},
             "gpu_launches": int(launches),
             "accuracy": accuracy,
+            "weak_scaling": weak,
             "clocks": clk,
             "roofline": roof,
             "rooflines": roofs,
             "costvolume": costvol,
             "tsdf": tsdf,
+            "extras": extras,
             "profiled_ms_per_step": ms_prof_total / args.steps,
             "kernels": [{"name": n, "launches": c, "ms": round(ms, 3)} for n, c, ms in sorted(prof, key=lambda x: -x[2])[:12]],
             "cpu_baseline": cpu,
@@ -477,6 +514,138 @@ def run_b200(args):
         }
         print(json.dumps(line), flush=True)
     sc.close()
+    weights.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_extras(batch, scene, sd, dev, mode):
+    """What the drop-in API costs around the render itself (wall clock with synchronize, one repetition after a warm-up):
+    ``ufo_scene_create`` (the repack of the view set's tensors) from device-resident and from host inputs, and
+    ``UFOReconRenderer.render_depth_map`` with the reference's CPU uniform stream and with device-side uniforms."""
+    from baseline import reference_arm      # only its to_device helper
+    from uforecon_b200.renderer import Scene, UFOReconRenderer
+    out = {}
+    b_dev, s_dev = reference_arm.to_device(batch, dev), reference_arm.to_device(scene, dev)
+    for name, (b, sc_) in (("scene_create_device_inputs_s", (b_dev, s_dev)), ("scene_create_host_inputs_s", (batch, scene))):
+        for it in range(2):
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            x = Scene(b, sc_["source_imgs_feat"], sc_["feature_volume"], sc_["match_feature"], dev)
+            torch.cuda.synchronize(dev)
+            dt = time.perf_counter() - t0
+            nbytes = x.device_bytes
+            x.close()
+        out[name] = dt
+    out["scene_device_bytes"] = int(nbytes)
+    ren = UFOReconRenderer(sd, dev, mode=mode)
+    ren.begin_scene(b_dev, s_dev["source_imgs_feat"], s_dev["feature_volume"], s_dev["match_feature"])
+    for name, kw in (("render_depth_map_device_rng_s", dict(device_rng=True)), ("render_depth_map_cpu_rng_s", dict(device_rng=False))):
+        for it in range(2 if kw["device_rng"] else 1):
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            d, c = ren.render_depth_map(b_dev, s_dev["source_imgs_feat"], s_dev["feature_volume"], s_dev["match_feature"], **kw)
+            d, c = d.cpu(), c.cpu()
+            dt = time.perf_counter() - t0
+        out[name] = dt
+    ren.close()
+    out["what"] = ("wall seconds; render_depth_map = the chunk loop of extract_geometry (model.py:814-831) for one 1600x1216 map incl. the "
+                   "device->host copy of depth/rgb; cpu_rng draws the reference's 2 x 64 uniforms per ray from torch's CPU generator")
+    return out
+
+
+def sweep_sources(n_images: int):
+    """Source views of every render view of a sweep: the 3 nearest cameras of the synthetic rig (what dtu_pairs.txt encodes
+    for the real rig: view-selection scores, best first)."""
+    import numpy as np
+    from uforecon_b200 import synthetic
+    rig = synthetic.make_rig(n_images)
+    eyes = np.stack([-m[:3, :3].T @ m[:3, 3] for m in rig])
+    out = []
+    for v in range(n_images):
+        d = np.linalg.norm(eyes - eyes[v], axis=1)
+        d[v] = np.inf
+        out.append([int(i) for i in np.argsort(d)[:3]])
+    return out
+
+
+def run_sweep(args):
+    """BASELINE configs[4]: a sweep of ``--sweep`` depth maps (49 = one DTU scan, the TSDF-fusion input), whole images
+    round-robin over the ranks (``dist.shard_images``).  Per image, inside the timed region: host->device copy of the image's
+    batch tensors (rays, source images, MVS depth), ``ufo_scene_create`` (the repack of its view set), the render of all
+    H*W rays, device->host copy of depth and colour.  The encoder outputs (features, volumes, match maps) are device-resident
+    synthetic tensors shared by all images - producing them is the PyTorch encoder's job, outside this path."""
+    import torch.distributed as dist
+    from baseline import reference_arm      # only its to_device helper
+    from uforecon_b200 import _lib, checkpoint, dist as ufodist, synthetic
+    from uforecon_b200.renderer import HotPathWeights, Scene, render_rays
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import __graft_entry__ as ge
+    ge.build()
+    mode = {"fp32": _lib.UFO_MODE_FP32, "tc16": _lib.UFO_MODE_TC_F16}[args.mode]
+    W, H = args.width, args.height
+    sd, ckpt_src = checkpoint.load_hot_path_state(os.path.join(ROOT, "pretrained", "uforecon.ckpt"))
+    weights = HotPathWeights(sd, dev)
+    mine = ufodist.shard_images(args.sweep, world, rank)
+    srcs = sweep_sources(args.sweep)
+    # host-side inputs of this rank's images (the dataloader's job), pinned; encoder outputs once, on the device
+    batches = []
+    scene = None
+    for v in mine:
+        b = synthetic.make_batch([v] + srcs[v][:args.nv - 1], (W, H))
+        if scene is None:
+            scene = reference_arm.to_device(synthetic.make_scene(b), dev)
+        b["depth_info"] = scene["depth_info"].cpu()
+        batches.append({k: (t.pin_memory() if torch.is_tensor(t) and t.numel() > 1024 else t) for k, t in b.items()})
+    n = H * W
+    u_c = torch.rand(64, n, device=dev)
+    u_f = torch.rand(64, n, device=dev)
+    depth_host = torch.empty(n).pin_memory()
+    rgb_host = torch.empty(n, 3).pin_memory()
+
+    def one_image(b):
+        bd = {k: (t.to(dev, non_blocking=True) if torch.is_tensor(t) else t) for k, t in b.items() if k not in ("proj_matrices",)}
+        sc = Scene(bd, scene["source_imgs_feat"], scene["feature_volume"], scene["match_feature"], dev)
+        r = render_rays(sc, weights, None, n, u_c, u_f, mode, ray_begin=0, want=("depth_z", "rgb"))
+        depth_host.copy_(r["depth_z"], non_blocking=True)
+        rgb_host.copy_(r["rgb"], non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        sc.close()
+
+    if batches:
+        one_image(batches[0])                      # warm-up
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for b in batches:
+        one_image(b)
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total = float(tt.item())
+    if rank == 0:
+        counts = [len(ufodist.shard_images(args.sweep, world, r)) for r in range(world)]
+        line = {"metric": METRIC, "value": args.sweep * n / total, "unit": UNIT, "n_gpus": world, "steps": 1, "warmup": 1,
+                "ms_per_step": total * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": {"fp32": "f32", "tc16": "f16"}[args.mode], "data": "synthetic",
+                "config": {"workload": f"{args.sweep}-view depth-map sweep of one synthetic scan at {W}x{H}, {args.nv} source views per image "
+                                       f"(3 nearest cameras), 64+64 samples/ray, images round-robin over {world} GPU(s) (BASELINE configs[4])",
+                           "per_image": "H2D of the image's batch tensors + ufo_scene_create + full-map render + D2H of depth/rgb",
+                           "checkpoint": ckpt_src, "mode": args.mode},
+                "sweep": {"images": args.sweep, "total_s": total, "images_per_rank": counts, "busiest_rank_images": max(counts),
+                          "s_per_image_on_busiest_rank": total / max(counts)},
+                "e2e": {"value": args.sweep * n / total, "unit": UNIT, "h2d_bytes_per_step": int(sum(t.numel() * 4 for t in batches[0].values() if torch.is_tensor(t)) * args.sweep),
+                        "d2h_bytes_per_step": 16 * n * args.sweep}}
+        print(json.dumps(line), flush=True)
     weights.close()
     if world > 1:
         dist.destroy_process_group()
@@ -676,15 +845,24 @@ def main():
     ap.add_argument("--width", type=int, default=int(os.environ.get("UFO_BENCH_W", "1600")))
     ap.add_argument("--height", type=int, default=int(os.environ.get("UFO_BENCH_H", "1216")))
     ap.add_argument("--nv", type=int, default=3)
-    ap.add_argument("--views", default="unfavorable", choices=["unfavorable", "favorable"])
+    ap.add_argument("--views", default=None, choices=["unfavorable", "favorable"],
+                    help="source view set at NV=3; default: unfavorable (1,16,36 = BASELINE configs[1]) at N=1, favorable "
+                         "(23,24,33 = configs[2], rays sharded over the GPUs) at N>1")
+    ap.add_argument("--sweep", type=int, default=0, help="BASELINE configs[4]: render this many depth maps (49), images round-robin over the ranks")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-chunks", type=int, default=4)
     ap.add_argument("--ref-chunks", type=int, default=2, help="--impl reference: 800-ray chunks per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-costvolume", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the scene-create / render_depth_map timings (N=1 extra)")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip the same-device extra (unmodified reference on cuda:0)")
     ap.add_argument("--rays", type=int, default=0, help="profiling aid: render only the first N rays of the map per step")
     args = ap.parse_args()
+    if args.views is None:
+        args.views = "unfavorable" if max(args.gpus, int(os.environ.get("WORLD_SIZE", "1"))) == 1 else "favorable"
+    if args.sweep > 0 and args.impl != "reference":
+        run_sweep(args)
+        return
     if args.impl == "reference":
         run_reference(args)
     else:
