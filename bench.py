@@ -396,10 +396,17 @@ def run_b200(args):
     # ---- e2e: host buffers, copies inside the timed region.  N = 1: ufo_render_rays_host.  N > 1: every rank uploads the
     #      uniforms of its row block from pinned host memory, renders, the blocks are gathered to rank 0 and rank 0 copies the
     #      assembled depth map to pinned host memory
+    if world > 1:      # this rank's block of the uniforms as its own contiguous pinned host / device buffers
+        u_c_hs = u_c_host[:, begin:begin + n_mine].contiguous().pin_memory()
+        u_f_hs = u_f_host[:, begin:begin + n_mine].contiguous().pin_memory()
+        u_c_ds, u_f_ds = torch.empty_like(u_c_hs, device=dev), torch.empty_like(u_f_hs, device=dev)
+
     def step_e2e_sharded():
-        u_c[:, begin:begin + n_mine].copy_(u_c_host[:, begin:begin + n_mine], non_blocking=True)
-        u_f[:, begin:begin + n_mine].copy_(u_f_host[:, begin:begin + n_mine], non_blocking=True)
-        got = step_sharded()
+        u_c_ds.copy_(u_c_hs, non_blocking=True)
+        u_f_ds.copy_(u_f_hs, non_blocking=True)
+        _lib.check(lib.ufo_render_rays(sc.handle, weights.handle, None, begin, n_mine, u_c_ds.data_ptr(), u_f_ds.data_ptr(), n_mine,
+                                       mode, C.byref(out), None, stream.cuda_stream))
+        got = ufodist.gather_depth_rgb(out_depthz[:n_mine], out_rgb[:n_mine], counts)
         if rank == 0:
             depth_host.copy_(got[0], non_blocking=True)
             rgb_host.copy_(got[1], non_blocking=True)

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define UFO_ABI_VERSION 1
+#define UFO_ABI_VERSION 2
 #define UFO_MAX_VIEWS 10
 #define UFO_N_STAGES 3
 #define UFO_N_COARSE 64 /* --test_sample_coarse, main.py:73 */
@@ -71,7 +71,7 @@ typedef struct {
   const float* source_imgs;  /* [dev] batch['source_imgs'][0]      [NV,3,H,W]           */
   const float* img_feats;    /* [dev] source_imgs_feat[0]          [NV,32,h,w]          */
   const float* depth_info;   /* [dev] batch['depth_info'][0]       [NV,H,W]             */
-  const float* match_feats;  /* [dev] match_feature[0][0]          [NV,(NV-1)*32,h,w]   */
+  const float* match_feats;  /* [dev] match_feature[0][0]          [NV,(NV-1)*32,h,w]  (NULL when match_pairs is given) */
   const float* vol_feat[UFO_N_STAGES];   /* [dev] feature_volume[stage]['feature_volume'] [NV,8,D,hs,ws] */
   const float* vol_weight[UFO_N_STAGES]; /* [dev] feature_volume[stage]['weight_volume']  [NV,1,D,hs,ws] */
   int32_t vol_d[UFO_N_STAGES], vol_h[UFO_N_STAGES], vol_w[UFO_N_STAGES];
@@ -83,6 +83,11 @@ typedef struct {
   const float* ray_o;            /* [host] batch['ray_o'][0]             [3]                 */
   const float* ray_d;            /* [dev]  batch['ray_d'][0]             [3,H*W]             */
   const float* cam_ray_d;        /* [dev]  batch['cam_ray_d'][0]         [3,H*W]             */
+  /* ABI 2: the compact pair maps, either/or with match_feats (exactly one of the two is non-NULL).  The reference's
+   * get_match_feat stores the map of every unordered view pair twice (FMT.py:197,308-309,
+   * TransMVSNet.py:362-366); an encoder that emits each pair once passes [NV(NV-1)/2, 32, h, w] here, pairs in the
+   * reference's enumeration order (a, b) for a in 0..NV-2, b in a+1..NV-1 (model.py:273-276). */
+  const float* match_pairs;      /* [dev]  [NV(NV-1)/2,32,h,w] or NULL */
 } UfoSceneDesc;
 
 /* Hot-path block of the checkpoint state dict; all [host] fp32, torch layout

@@ -25,12 +25,12 @@ def test_header_symbols_exported(lib):
     raw = C.CDLL(_lib.LIB_PATH)
     for s in declared:
         assert hasattr(raw, s), f"{s} not exported"
-    assert lib.ufo_abi_version() == 1
+    assert lib.ufo_abi_version() == 2
 
 
 def test_struct_layout_matches_header():
     # pointer-sized / int32 fields only, natural alignment: sizes derive from the header by construction
-    assert C.sizeof(_lib.UfoSceneDesc) == 5 * 4 + 4 + 4 * 8 + 6 * 8 + 9 * 4 + 4 + 8 * 8
+    assert C.sizeof(_lib.UfoSceneDesc) == 5 * 4 + 4 + 4 * 8 + 6 * 8 + 9 * 4 + 4 + 9 * 8
     assert C.sizeof(_lib.UfoLoftrLayer) == 10 * 8
     assert C.sizeof(_lib.UfoMlp3) == 6 * 8
     assert C.sizeof(_lib.UfoWeightsDesc) == 2 * 80 + 3 * 48 + 3 * 8 + 8

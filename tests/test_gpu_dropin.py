@@ -201,3 +201,30 @@ def test_start_idx_selects_the_w2c_rows(small):
         sc.close()
     w.close()
     assert torch.equal(out[0], out[1])
+
+
+@pytest.mark.parametrize("nv", [3, 5])
+def test_compact_pair_maps_equal_reference_layout(nv):
+    """N2: the match maps given once per pair ([NV(NV-1)/2,32,h,w]) render bit-identically to the reference's 2x redundant
+    [NV,(NV-1)*32,h,w] stack built from the same maps."""
+    from uforecon_b200.renderer import HotPathWeights, Scene, render_rays
+    views = synthetic.UNFAVORABLE_VIEWS if nv == 3 else synthetic.TEN_VIEW_LIST[:nv]
+    batch, scene, sd = make_case(views, (96, 64))
+    w = HotPathWeights(sd)
+    u_c, u_f = synthetic.sampler_uniforms(300, seed=4)
+    outs = []
+    for kw in (dict(), dict(pair_maps=scene["pair_maps"])):
+        sc = Scene(batch, scene["source_imgs_feat"], scene["feature_volume"], None if kw else scene["match_feature"], **kw) if kw else \
+            Scene(batch, scene["source_imgs_feat"], scene["feature_volume"], scene["match_feature"])
+        for mode in (UFO_MODE_FP32, UFO_MODE_TC):
+            r = render_rays(sc, w, None, 300, u_c, u_f, mode, ray_begin=900, want=("depth", "rgb"), taps=("sim8",))
+            outs.append({k: v.clone() for k, v in r.items()})
+        if kw:
+            assert sc.device_bytes < ref_bytes
+        else:
+            ref_bytes = sc.device_bytes
+        sc.close()
+    w.close()
+    for a, b in ((outs[0], outs[2]), (outs[1], outs[3])):
+        for k in a:
+            assert torch.equal(a[k], b[k]), k

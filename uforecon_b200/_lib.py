@@ -31,7 +31,7 @@ class UfoSceneDesc(C.Structure):
         ("vol_d", C.c_int32 * UFO_N_STAGES), ("vol_h", C.c_int32 * UFO_N_STAGES), ("vol_w", C.c_int32 * UFO_N_STAGES),
         ("source_poses", C.c_void_p), ("source_poses_inv", C.c_void_p), ("ref_pose_inv", C.c_void_p),
         ("w2cs", C.c_void_p), ("near_fars", C.c_void_p), ("ray_o", C.c_void_p),
-        ("ray_d", C.c_void_p), ("cam_ray_d", C.c_void_p),
+        ("ray_d", C.c_void_p), ("cam_ray_d", C.c_void_p), ("match_pairs", C.c_void_p),
     ]
 
 
@@ -134,7 +134,7 @@ def load() -> C.CDLL:
     lib.ufo_tsdf_mesh_destroy.argtypes = [C.c_void_p]
     lib.ufo_tsdf_mesh_destroy.restype = None
     lib.ufo_profile_end.argtypes = [C.POINTER(UfoProfileEntry), C.c_int32, C.POINTER(C.c_int32)]
-    if lib.ufo_abi_version() != 1:
+    if lib.ufo_abi_version() != 2:
         raise UfoError(f"ABI version mismatch: library {lib.ufo_abi_version()} != binding 1")
     _lib = lib
     return lib

@@ -110,3 +110,50 @@ def feature_grid(feats: torch.Tensor, batch: Dict[str, torch.Tensor], linear: Di
         _lib.check(lib.ufo_feature_grid(f.data_ptr(), NV, h, w, poses.data_ptr(), volume_reso, C.byref(m), out.data_ptr(), _stream_ptr(dev)))
         torch.cuda.current_stream(dev).synchronize()
     return out
+
+
+class FusedDepthNet(torch.nn.Module):
+    """``DepthNet`` with its warp / correlate / view-weight loop (TransMVSNet.py:69-100) replaced by kernel 1; everything
+    after the similarity volume - the 3-D regulariser, softmax, winner-take-all depth, confidence - is the reference's own code
+    path restated line by line (TransMVSNet.py:102-121).  Same call signature and return values as ``DepthNet.forward``."""
+
+    def __init__(self, depthnet: torch.nn.Module):
+        super().__init__()
+        self.depthnet = depthnet
+
+    def forward(self, features, proj_matrices, depth_values, num_depth, cost_regularization, prob_volume_init=None,
+                view_weights=None, mvs_volume_only=False):
+        assert depth_values.shape[1] == num_depth
+        sd = {PW + k: v for k, v in self.depthnet.pixel_wise_net.state_dict().items()}
+        dev = features[0].device
+        sim, vw = similarity_volume(list(features), proj_matrices, depth_values, sd, view_weights=view_weights, device=dev)
+        cost_reg = cost_regularization(sim)                                    # TransMVSNet.py:103
+        if mvs_volume_only:
+            return None
+        prob_volume_pre = cost_reg.squeeze(1)
+        if prob_volume_init is not None:
+            prob_volume_pre = prob_volume_pre + prob_volume_init
+        prob_volume = torch.exp(torch.nn.functional.log_softmax(prob_volume_pre, dim=1))
+        idx = torch.argmax(prob_volume, dim=1, keepdim=True).type(torch.long)  # depth_wta, fmt/module.py:561-565
+        depth = torch.gather(depth_values, 1, idx).squeeze(1)
+        with torch.no_grad():
+            conf = torch.max(prob_volume, dim=1)[0]
+        out = {"depth": depth, "photometric_confidence": conf, "prob_volume": prob_volume, "depth_values": depth_values,
+               "cost_volume": cost_reg}
+        if view_weights is None:
+            return out, vw.detach()
+        return out
+
+
+import contextlib  # noqa: E402
+
+
+@contextlib.contextmanager
+def fused_cost_volume(transmvsnet: torch.nn.Module):
+    """Within the block the cascade of ``TransMVSNet.forward`` builds its three cost volumes with kernel 1."""
+    orig = transmvsnet.DepthNet
+    transmvsnet.DepthNet = FusedDepthNet(orig)
+    try:
+        yield transmvsnet.DepthNet
+    finally:
+        transmvsnet.DepthNet = orig

@@ -387,7 +387,9 @@ extern "C" int ufo_scene_create(const UfoSceneDesc* d, UfoScene** out, void* str
   if (d->n_views < 2 || d->n_views > UFO_MAX_VIEWS)
     return fail(UFO_EINVAL, "ufo_scene_create: n_views=%d outside [2,%d]", d->n_views, UFO_MAX_VIEWS);
   if (d->img_h <= 0 || d->img_w <= 0 || d->feat_h <= 0 || d->feat_w <= 0) return fail(UFO_EINVAL, "ufo_scene_create: bad size");
-  if (!d->source_imgs || !d->img_feats || !d->depth_info || !d->match_feats || !d->source_poses || !d->source_poses_inv ||
+  if ((d->match_feats != nullptr) == (d->match_pairs != nullptr))
+    return fail(UFO_EINVAL, "ufo_scene_create: exactly one of match_feats (reference layout) and match_pairs (compact) must be given");
+  if (!d->source_imgs || !d->img_feats || !d->depth_info || !d->source_poses || !d->source_poses_inv ||
       !d->ref_pose_inv || !d->w2cs || !d->near_fars || !d->ray_o || !d->ray_d || !d->cam_ray_d)
     return fail(UFO_EINVAL, "ufo_scene_create: null tensor pointer");
   for (int s = 0; s < 3; ++s)
@@ -414,13 +416,17 @@ extern "C" int ufo_scene_create(const UfoSceneDesc* d, UfoScene** out, void* str
   float* feat_cl; float4* rgbd; float* match_cl;
   if ((e = dalloc(sizeof(float) * nv * hw * kFeatC, (void**)&feat_cl))) return e;
   if ((e = dalloc(sizeof(float4) * nv * HW, (void**)&rgbd))) return e;
-  if ((e = dalloc(sizeof(float) * nv * (nv - 1) * hw * kFeatC, (void**)&match_cl))) return e;
+  const int n_pairs = nv * (nv - 1) / 2;
+  const bool compact = d->match_pairs != nullptr;
+  if ((e = dalloc(sizeof(float) * (compact ? n_pairs : nv * (nv - 1)) * hw * kFeatC, (void**)&match_cl))) return e;
   if ((e = repack_cl<kFeatC>(d->img_feats, feat_cl, hw, nv, st))) return e;
-  if ((e = repack_cl<kFeatC>(d->match_feats, match_cl, hw, nv * (nv - 1), st))) return e;
+  if ((e = repack_cl<kFeatC>(compact ? d->match_pairs : d->match_feats, match_cl, hw, compact ? n_pairs : nv * (nv - 1), st))) return e;
   UFO_KERNEL("k_pack_rgbd", st, k_pack_rgbd<<<cdiv(HW * nv, 256), 256, 0, st>>>(d->source_imgs, d->depth_info, rgbd, HW, nv));
   D.feat_cl = feat_cl; D.rgbd_cl = rgbd; D.match_cl = match_cl;
-  {  // the reference stores every pair map twice; when the two copies are bit-identical both samples of a
-     // pair read the same copy, which halves the working set of the dominant gather at large NV
+  if (compact) {
+    D.match_sym = 2;
+  } else {  // the reference stores every pair map twice; when the two copies are bit-identical both samples of a
+            // pair read the same copy, which halves the working set of the dominant gather at large NV
     int* flag = nullptr;           // owned by the scene (4 bytes), so that no return path can leak it
     if ((e = dalloc(sizeof(int), (void**)&flag))) return e;
     UFO_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
@@ -430,6 +436,15 @@ extern "C" int ufo_scene_create(const UfoSceneDesc* d, UfoScene** out, void* str
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
     if (ce != cudaSuccess) { return fail(UFO_ECUDA, "ufo_scene_create: %s", cudaGetErrorString(ce)); }
     D.match_sym = differ ? 0 : 1;
+  }
+  {  // slot table: pairs in the reference's enumeration order (model.py:273-276)
+    int pi = 0;
+    for (int a2 = 0; a2 < nv; ++a2)
+      for (int b2 = a2 + 1; b2 < nv; ++b2, ++pi) {
+        const int sa = a2 * (nv - 1) + (b2 - 1), sb = b2 * (nv - 1) + a2;
+        D.match_slot[a2][b2] = (unsigned char)(compact ? pi : sa);
+        D.match_slot[b2][a2] = (unsigned char)(compact ? pi : (D.match_sym ? sa : sb));
+      }
   }
   for (int s = 0; s < 3; ++s) {
     D.vd[s] = d->vol_d[s]; D.vh[s] = d->vol_h[s]; D.vw[s] = d->vol_w[s];

@@ -27,9 +27,11 @@ struct SceneDev {
   int vd[3], vh[3], vw[3];
   const float* feat_cl;         // [NV][h][w][32]
   const float4* rgbd_cl;        // [NV][H][W] (r,g,b,mvs_depth)
-  const float* match_cl;        // [NV][NV-1][h][w][32]
-  int match_sym;                // 1: slot (b, a) holds the same map as slot (a, b-1) for every pair a < b (SURVEY.md F8,
-                                //    verified bit for bit at scene creation): both samples of a pair then read slot (a, b-1)
+  const float* match_cl;        // [slots][h][w][32]: NV*(NV-1) slots in the reference's layout, NV*(NV-1)/2 for compact pair maps
+  unsigned char match_slot[kMaxV][kMaxV];  // [v][o]: slot of the map sampled at view v's projection for the pair {v, o}.  Reference
+                                // layout: slot v*(NV-1) + (o > v ? o-1 : o); when the two copies of every pair map are bit-identical
+                                // (verified at scene creation) or the maps were given compact, both views share one slot
+  int match_sym;                // 0: two slots per pair, 1: copies identical (one slot read), 2: compact input
   const float* vol_feat_cl[3];  // [NV][D][hs][ws][8]
   const float* vol_w[3];        // [NV][D][hs][ws]
   const float* ray_d;           // [3][H*W]

@@ -193,8 +193,8 @@ __device__ __forceinline__ void gather_point(const SceneDev& sc, float x, float 
       for (int b = a + 1; b < NV; ++b) {
         const BilTaps ta = bil_setup<true, true>(u[a], v[a], sc.h, sc.w);
         const BilTaps tb = bil_setup<true, true>(u[b], v[b], sc.h, sc.w);
-        const float4 fa = bil_fetch32(sc.match_cl + (size_t)(a * (NV - 1) + (b - 1)) * fstride, ta, j);
-        const float4 fb = bil_fetch32(sc.match_cl + (size_t)(sc.match_sym ? a * (NV - 1) + (b - 1) : b * (NV - 1) + a) * fstride, tb, j);
+        const float4 fa = bil_fetch32(sc.match_cl + (size_t)sc.match_slot[a][b] * fstride, ta, j);
+        const float4 fb = bil_fetch32(sc.match_cl + (size_t)sc.match_slot[b][a] * fstride, tb, j);
         acc += cos4(fa, fb);
         ++npairs;
       }

@@ -212,6 +212,12 @@ __device__ __forceinline__ long long tc_slot(long long p, int half) { return (p 
 // reduce-scatter over the group leaves channel j of the interpolated feature in lane j (7 shuffles) and the
 // interpolated weight-volume value in every lane (3 shuffles).  Same taps and weights as tri_fetch, other summation
 // order.  Split in two halves so that the loads of several volumes can be in flight together.
+// one 256-bit read-only load (sm_100: LDG.E.256): an 8-channel fp32 voxel is one 32-byte sector
+__device__ __forceinline__ void ldg8(const float* p, float4& a, float4& b) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p));
+}
 struct TriTap {
   size_t idx;     // voxel index of this lane's tap (0 when the tap is out of range)
   float wgt;      // trilinear weight of the tap (0 when out of range)
@@ -372,8 +378,7 @@ __global__ void __launch_bounds__(256, UFO_GATHER_MINB) k_gather_tc(SceneDev sc,
         for (int s = 0; s < 3; ++s) {          // all 9 loads of this view in flight together
           const size_t vox = (size_t)sc.vd[s] * sc.vh[s] * sc.vw[s];
           const float* vf = sc.vol_feat_cl[s] + (n * vox + tp[s].idx) * kVolC;
-          va[s] = ldg4(vf);
-          vb[s] = ldg4(vf + 4);
+          ldg8(vf, va[s], vb[s]);            // the whole 32-byte voxel in one 256-bit load
           vwt[s] = __ldg(sc.vol_w[s] + n * vox + tp[s].idx);
         }
 #pragma unroll
@@ -428,8 +433,8 @@ __global__ void __launch_bounds__(256, UFO_GATHER_MINB) k_gather_tc(SceneDev sc,
 #pragma unroll
         for (int b = a + 1; b < NV; ++b) {
           const BilTaps tb = taps_of(2 * NV + b);
-          const float4 fa = bil_fetch32(sc.match_cl + (size_t)(a * (NV - 1) + (b - 1)) * fstride, ta, j);
-          const float4 fb = bil_fetch32(sc.match_cl + (size_t)(sc.match_sym ? a * (NV - 1) + (b - 1) : b * (NV - 1) + a) * fstride, tb, j);
+          const float4 fa = bil_fetch32(sc.match_cl + (size_t)sc.match_slot[a][b] * fstride, ta, j);
+          const float4 fb = bil_fetch32(sc.match_cl + (size_t)sc.match_slot[b][a] * fstride, tb, j);
           acc += cos4(fa, fb);
         }
       }

@@ -109,7 +109,10 @@ class Scene:
 
     def __init__(self, batch: Dict[str, torch.Tensor], source_imgs_feat: torch.Tensor,
                  feature_volume: Dict[str, Dict[str, torch.Tensor]], match_feature: Sequence[torch.Tensor],
-                 device: Optional[torch.device] = None):
+                 device: Optional[torch.device] = None, pair_maps: Optional[torch.Tensor] = None):
+        """``pair_maps`` [NV(NV-1)/2, 32, h, w]: the cross-view match maps with every pair stored once (pairs in the reference's
+        order, model.py:273-276) - what an encoder without the reference's 2x redundant stack emits; when
+        given, ``match_feature`` may be None."""
         self.lib = _lib.load()
         self.device = torch.device(device if device is not None else "cuda")
         if source_imgs_feat.shape[0] != 1:
@@ -118,8 +121,11 @@ class Scene:
         _, _, FC, h, w = source_imgs_feat.shape
         if FC != 32:
             raise ValueError(f"feature maps must have 32 channels, got {FC}")
-        if tuple(match_feature[0].shape) != (1, NV, (NV - 1) * 32, h, w):
-            raise ValueError(f"match_feature[0] shape {tuple(match_feature[0].shape)} != {(1, NV, (NV - 1) * 32, h, w)}")
+        if pair_maps is not None:
+            if tuple(pair_maps.shape) != (NV * (NV - 1) // 2, 32, h, w):
+                raise ValueError(f"pair_maps shape {tuple(pair_maps.shape)} != {(NV * (NV - 1) // 2, 32, h, w)}")
+        elif match_feature is None or tuple(match_feature[0].shape) != (1, NV, (NV - 1) * 32, h, w):
+            raise ValueError(f"match_feature[0] must be {(1, NV, (NV - 1) * 32, h, w)}")
         if "depth_info" not in batch:
             raise KeyError("batch['depth_info'] missing (set by extract_geometry, model.py:806-808)")
         # every tensor the kernels index with NV / H*W strides is checked here: the library trusts these shapes
@@ -162,7 +168,10 @@ class Scene:
         d.source_imgs = dv(batch["source_imgs"][0])
         d.img_feats = dv(source_imgs_feat[0])
         d.depth_info = dv(batch["depth_info"][0])
-        d.match_feats = dv(match_feature[0][0])
+        if pair_maps is not None:
+            d.match_pairs = dv(pair_maps)
+        else:
+            d.match_feats = dv(match_feature[0][0])
         for i, st in enumerate(STAGES):
             fv, wv = feature_volume[st]["feature_volume"], feature_volume[st]["weight_volume"]
             if fv.dim() != 5 or wv.dim() != 5 or fv.shape[0] != NV or fv.shape[1] != 8 or tuple(wv.shape) != (NV, 1) + tuple(fv.shape[2:]):
