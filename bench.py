@@ -692,14 +692,19 @@ def measure_accuracy(lib, sc, weights, batch, mode, u_c, u_f, n_rays, W, H, stre
 
 
 def _ncu_traffic():
-    """DRAM bytes per sample point of the dominant kernels from the committed ncu --set full capture
-    (profiles/ncu_traffic.json), or {}; scaled to this run's average launch in roofline_entries."""
+    """Per kernel family: DRAM bytes per launch and unit utilisations from the committed ncu --set full capture at the default
+    chunk size (profiles/ncu_traffic.json, written by tools/ncu_traffic.py), or {}."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     return json.load(open(p)) if os.path.exists(p) else {}
 
 
 def roofline_entries(prof, args, n_rays, pk):
-    """One roofline entry per kernel family of the timed region, largest share first."""
+    """One roofline entry per kernel family of the timed region, largest share first.
+
+    Tensor kernels: algorithmic FLOPs of the points the launches process / live CUDA-event time, against the sustained bf16
+    peak.  The gather: the DRAM bytes it really moves (ncu capture at the same chunk size) / live time against the HBM copy
+    peak - a small fraction, because its limiter is not HBM: the texel / voxel tap bytes it pulls through L1 (``tap_gbs``) and
+    ncu's L1 / issue utilisation are reported beside it."""
     if not prof:
         return []
     total_ms = sum(ms for _, _, ms in prof)
@@ -711,9 +716,14 @@ def roofline_entries(prof, args, n_rays, pk):
     pts_pt = n_rays * (128 if args.mode != "fp32" else 192) * args.steps
     pts = pts_ray
     traffic = _ncu_traffic()
+    same_cfg = args.nv == 3 and args.width == 1600 and args.height == 1216 and args.rays <= 0
     out = []
     for name, cnt, ms in sorted(prof, key=lambda x: -x[2]):
         bound, unit, work, note = "tensor", "TFLOP/s", None, None
+        fam = name.split("<")[0]
+        t = traffic.get(fam) if isinstance(traffic.get(fam), dict) and same_cfg else None
+        avg_s = ms * 1e-3 / cnt
+        extra = {}
         if name.startswith("k_view_tc"):
             work = pts_pt * (fl["view"] + fl["radiance"])
         elif name.startswith("k_ray_tc"):
@@ -724,23 +734,34 @@ def roofline_entries(prof, args, n_rays, pk):
             work = 2.0 * rows * k * n
         elif name.startswith("k_gather"):
             bound, unit = "hbm", "GB/s"
-            work = pts_pt * tap_bytes_per_point(nv)
-            note = "algorithmic bytes = texel/voxel tap bytes (L1/L2 level); compulsory HBM bytes are the 4.2 GB scene"
+            tap = pts_pt * tap_bytes_per_point(nv)
+            extra["tap_gbs"] = tap / cnt / avg_s / 1e9
+            extra["tap_bytes_per_launch"] = tap / cnt
+            if t:
+                work = t["bytes_per_launch"] * cnt
+                note = ("achieved = DRAM bytes the launch moves (ncu, same chunk size: 70 % of them are the token / colour / direction "
+                        "rows it writes for the view stage) / live launch time; the limiter is L1 + issue, not HBM: see tap_gbs "
+                        "(texel / voxel tap bytes pulled through L1) and the ncu utilisations")
+            else:
+                work = tap
+                note = "no ncu capture for this configuration: achieved = texel / voxel tap bytes (L1 / L2 level), NOT DRAM bytes"
         if work is None:
             continue
-        avg_s = ms * 1e-3 / cnt
         per_launch = work / cnt
         achieved = per_launch / avg_s / (1e12 if bound == "tensor" else 1e9)
         peak = pk["tf_sustained"] if bound == "tensor" else pk["hbm_gbs"]
         e = {"kernel": name, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
-             "traffic": (traffic[name.split("<")[0]]["bytes_per_point"] * (pts_ray if name.startswith("k_ray_tc") else pts_pt) / cnt
-                         if isinstance(traffic.get(name.split("<")[0]), dict) else None),
+             "traffic": t["bytes_per_launch"] if t else None,
              "peak_source": pk["src"] + (" (sustained bf16)" if bound == "tensor" else " (copy)"),
              "launches": cnt, "avg_launch_ms": avg_s * 1e3, "share_of_step": ms / total_ms,
              "algorithmic_work_per_launch": per_launch,
              "work_basis": "algorithmic work of the sample points the launches process (ray stage 192 per ray; gathers and "
                            "view stage 128 per ray in the tensor-core modes, where the fine pass reuses the coarse results; "
                            "the reference evaluates 192)"}
+        if t:
+            e["ncu"] = {k: round(t[k], 2) for k in ("l1_throughput_pct", "l2_throughput_pct", "issue_active_pct", "tensor_pipe_active_pct",
+                                                    "dram_throughput_pct") if k in t}
+        e.update(extra)
         if note:
             e["note"] = note
         out.append(e)

@@ -40,20 +40,29 @@ def test_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
 
 
-def test_roofline_entries_scale_ncu_traffic_to_the_launch():
+def test_roofline_entries_bookkeeping():
+    """tensor kernels: algorithmic FLOPs per launch; the gather: DRAM bytes of the ncu capture (only when the configuration is
+    the captured one), tap bytes reported beside it - never tap bytes against the HBM peak under the name of a roofline."""
     import argparse
     import bench
-    args = argparse.Namespace(nv=3, steps=2, mode="tc16")
     n_rays = 1000
     prof = [("k_view_tc<3, 0>", 4, 8.0), ("k_ray_tc<128, 0>", 4, 6.0), ("k_gather_tc<3, 0>", 4, 6.0), ("k_render<kNS>", 2, 0.1)]
     pk = {"tf_sustained": 1394.5, "hbm_gbs": 6546.6, "src": "test"}
-    roofs = bench.roofline_entries(prof, args, n_rays, pk)
-    by = {r["kernel"].split("<")[0]: r for r in roofs}
-    assert set(by) == {"k_view_tc", "k_ray_tc", "k_gather_tc"} and roofs[0]["kernel"].startswith("k_view_tc")
-    fl = bench.flops_per_point(3)
-    assert abs(by["k_view_tc"]["algorithmic_work_per_launch"] - n_rays * 128 * 2 * (fl["view"] + fl["radiance"]) / 4) < 1
-    assert abs(by["k_ray_tc"]["algorithmic_work_per_launch"] - n_rays * 192 * 2 * (fl["ray"] + fl["density"]) / 4) < 1
     t = bench._ncu_traffic()
-    assert abs(by["k_ray_tc"]["traffic"] - t["k_ray_tc"]["bytes_per_point"] * n_rays * 192 * 2 / 4) < 1
-    assert by["k_gather_tc"]["bound"] == "hbm" and by["k_view_tc"]["bound"] == "tensor"
-    assert abs(sum(r["share_of_step"] for r in roofs) - 20.0 / 20.1) < 1e-9
+    for cfg_matches in (True, False):
+        args = argparse.Namespace(nv=3, steps=2, mode="tc16", width=1600 if cfg_matches else 416, height=1216, rays=0)
+        roofs = bench.roofline_entries(prof, args, n_rays, pk)
+        by = {r["kernel"].split("<")[0]: r for r in roofs}
+        assert set(by) == {"k_view_tc", "k_ray_tc", "k_gather_tc"} and roofs[0]["kernel"].startswith("k_view_tc")
+        fl = bench.flops_per_point(3)
+        assert abs(by["k_view_tc"]["algorithmic_work_per_launch"] - n_rays * 128 * 2 * (fl["view"] + fl["radiance"]) / 4) < 1
+        assert abs(by["k_ray_tc"]["algorithmic_work_per_launch"] - n_rays * 192 * 2 * (fl["ray"] + fl["density"]) / 4) < 1
+        assert by["k_gather_tc"]["bound"] == "hbm" and by["k_view_tc"]["bound"] == "tensor"
+        assert abs(by["k_gather_tc"]["tap_bytes_per_launch"] - n_rays * 128 * 2 * bench.tap_bytes_per_point(3) / 4) < 1
+        if cfg_matches and "k_gather_tc" in t:
+            assert by["k_gather_tc"]["traffic"] == t["k_gather_tc"]["bytes_per_launch"]
+            assert by["k_gather_tc"]["algorithmic_work_per_launch"] == t["k_gather_tc"]["bytes_per_launch"]
+            assert by["k_ray_tc"]["traffic"] == t["k_ray_tc"]["bytes_per_launch"] and "ncu" in by["k_view_tc"]
+        else:
+            assert by["k_gather_tc"]["traffic"] is None and "NOT DRAM" in by["k_gather_tc"]["note"]
+        assert abs(sum(r["share_of_step"] for r in roofs) - 20.0 / 20.1) < 1e-9

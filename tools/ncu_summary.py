@@ -18,7 +18,8 @@ WANT = [("gpu__time_duration.sum", "duration"), ("launch__grid_size", "grid"), (
 
 def main():
     rep = sys.argv[1]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # a .ncu-rep, or the CSV `ncu -i rep --page raw --csv` exported on the GPU box (the reports exceed gpurun's copy-back limit)
+    raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}

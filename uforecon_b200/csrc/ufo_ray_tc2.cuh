@@ -46,6 +46,29 @@ static_assert(R2_SMEM <= 115712, "ray-stage (v2) shared memory: two CTAs must fi
 static_assert(R2_SCR + 2 * 128 * 8 <= R2_SLOT, "scratch overlaps the weight slots");
 }  // namespace tc
 
+namespace tc {
+// LayerNorm partial (sum, sum of squares) over NC chunks of 8 values, four independent accumulation chains per statistic
+template <int NC>
+__device__ __forceinline__ float2 ln_partial(const float2 (*v)[4]) {
+  float2 s[4], q2[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    s[k] = v[0][k];
+    q2[k] = __fmul2_rn(v[0][k], v[0][k]);
+  }
+#pragma unroll
+  for (int i = 1; i < NC; ++i)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      s[k] = __fadd2_rn(s[k], v[i][k]);
+      q2[k] = __ffma2_rn(v[i][k], v[i][k], q2[k]);
+    }
+  const float2 st = __fadd2_rn(__fadd2_rn(s[0], s[1]), __fadd2_rn(s[2], s[3]));
+  const float2 qt = __fadd2_rn(__fadd2_rn(q2[0], q2[1]), __fadd2_rn(q2[2], q2[3]));
+  return make_float2(st.x + st.y, qt.x + qt.y);
+}
+}  // namespace tc
+
 // SN = 128: one ray per tile; SN = 64: two rays per tile.
 template <int SN, bool BF16>
 __global__ void __launch_bounds__(256, 2)
@@ -140,24 +163,33 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
       b = __ldg(reinterpret_cast<const float4*>(pe_table + (r % SN) * 8 + 4));
     }
   };
-  // chunks [c0, c1) of the 16-bit x operand -> TMEM columns col0 + 4 c
-  auto x_stage = [&](long long ir, int c0, int c1, uint32_t col0) {
+  // This thread's half of the fp32 input row, chunks 6 g .. 6 g + 5 (g = 1: chunk 10 is the order encoding, chunk 11 zero):
+  // the loads are ISSUED ahead of an MMA wait and consumed after it, so that their L2 latency is not exposed
+  float4 xr[12];
+  auto x_issue = [&](long long ir) {
 #pragma unroll
-    for (int c = c0; c < c1; ++c) {
-      float4 a, b;
-      x_chunk(ir, c, a, b);
-      umma::tmem_st4(tl + col0 + 4 * c, umma::pack2<BF16>(a.x, a.y), umma::pack2<BF16>(a.z, a.w), umma::pack2<BF16>(b.x, b.y),
-                     umma::pack2<BF16>(b.z, b.w));
+    for (int i = 0; i < 6; ++i) x_chunk(ir, 6 * g + i, xr[2 * i], xr[2 * i + 1]);
+  };
+  // the loaded chunks as 16-bit operand chunks -> TMEM columns col0 + 4 c   (n_chunks: 12 for the QKV operand, 11 for [x | LN1])
+  auto x_store = [&](uint32_t col0, int n_chunks) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const int c = 6 * g + i;
+      if (c < n_chunks)
+        umma::tmem_st4(tl + col0 + 4 * c, umma::pack2<BF16>(xr[2 * i].x, xr[2 * i].y), umma::pack2<BF16>(xr[2 * i].z, xr[2 * i].w),
+                       umma::pack2<BF16>(xr[2 * i + 1].x, xr[2 * i + 1].y), umma::pack2<BF16>(xr[2 * i + 1].z, xr[2 * i + 1].w));
     }
   };
+  if ((long long)blockIdx.x < n_tiles) x_issue(in_row_of(blockIdx.x));
 
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long prow = tile * 128 + r;           // this thread's token: ray prow / SN, sorted sample prow % SN
     const bool row_ok = prow < P;
     const long long in_row = in_row_of(tile);
     const bool has_next = tile + (long long)gridDim.x < n_tiles;
+    const long long in_row_nx = has_next ? in_row_of(tile + gridDim.x) : -1;      // its perm lookup completes long before it is used
     // ---- R0: x = [view-stage token 0 output | order encoding | 0] -> 16-bit A operand in TMEM (chunks 6 g .. 6 g + 5)
-    if (g == 0) x_stage(in_row, 0, 6, C_X); else x_stage(in_row, 6, 12, C_X);
+    x_store(C_X, 12);                                            // loads issued by the previous tile (or the prologue)
     umma::tmem_st_wait();
     umma::tc_fence_before();
     __syncthreads();
@@ -170,7 +202,6 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     }
     mma_wait();
     if (t == 0) load_piece(2);                                   // merge weights -> the slot Wkv leaves
-    // ---- R1b: q = x . Wq^T, issued now so that it runs under the k/v epilogue (its accumulator aliases k: see below)
     // ---- R2a: K' = elu(k)+1, V' = v -> MN-major operand tiles in shared memory   (linear_attention.py:36-41)
     {
       auto r2a = [&](auto GGc) {
@@ -313,6 +344,7 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
       issue_ts(D_MRG, C_M, b, 96, 96, 6, 0);
       umma::commit(bar);
     }
+    x_issue(in_row);                                             // x again, for the [x | LN1] operand: under the merge GEMM
     mma_wait();
     if (t == 0) load_piece(4);                                   // mlp.0 rows 96..175
     // ---- R8: LayerNorm 1 -> second half of the concat operand [x | LN1] (chunks 11..21); x re-staged as chunks 0..10
@@ -324,16 +356,8 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
 #pragma unroll
         for (int i = 0; i < NC; ++i) tmem_ld8p(tl + D_MRG + 8 * (C0 + i), v[i]);
         umma::tmem_ld_wait();
-        float2 s = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int i = 0; i < NC; ++i)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            s = __fadd2_rn(s, v[i][k]);
-            q2 = __ffma2_rn(v[i][k], v[i][k], q2);
-          }
-        red[GG * 128 + r] = make_float2(s.x + s.y, q2.x + q2.y);
-        if (GG == 0) x_stage(in_row, 0, 6, C_XL); else x_stage(in_row, 6, 11, C_XL);      // under the barrier
+        red[GG * 128 + r] = ln_partial<NC>(v);
+        x_store(C_XL, 11);
         umma::tc_fence_before();
         __syncthreads();
         const float2 st = ln2_stats(red, r, 1.f / 88.f);
@@ -411,6 +435,7 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
       issue_ts(D_ML2, C_H1, b, 96, 96, 11, 0);
       umma::commit(bar);
     }
+    x_issue(in_row);                                             // fp32 residual input of this row: under the mlp.2 GEMM
     mma_wait();
     if (t == 0 && has_next) load_piece(0);                       // the next tile's Wkv
     // ---- R12: LayerNorm 2, residual in fp32 from the fp32 input, split hi/lo for the SRDF head
@@ -422,23 +447,14 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
 #pragma unroll
         for (int i = 0; i < NC; ++i) tmem_ld8p(tl + D_ML2 + 8 * (C0 + i), v[i]);
         umma::tmem_ld_wait();
-        float2 s = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int i = 0; i < NC; ++i)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            s = __fadd2_rn(s, v[i][k]);
-            q2 = __ffma2_rn(v[i][k], v[i][k], q2);
-          }
-        red[GG * 128 + r] = make_float2(s.x + s.y, q2.x + q2.y);
+        red[GG * 128 + r] = ln_partial<NC>(v);
         umma::tc_fence_before();
         __syncthreads();
         const float2 st = ln2_stats(red, r, 1.f / 88.f);
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
           const int c = C0 + i;
-          float4 xa, xb;
-          x_chunk(in_row, c, xa, xb);                            // fp32 residual input of this row
+          const float4 xa = xr[2 * i], xb = xr[2 * i + 1];        // chunk c = 6 g + i of the fp32 input row
           float2 o2[4];
           ln_apply(v[i], st, prm.n2w + 8 * c, prm.n2b + 8 * c, o2);
           const float o[8] = {xa.x + o2[0].x, xa.y + o2[0].y, xa.z + o2[1].x, xa.w + o2[1].y,
@@ -474,6 +490,7 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
       issue_ts(D_DEN, C_RHI, b + 32 * 96 * 2, 32, 32, 6, 1);
       umma::commit(bar);
     }
+    if (has_next) x_issue(in_row_nx);                            // the next tile's x: under the SRDF-head GEMM and its tail
     mma_wait();
     if (t == 0 && has_next) load_piece(1);                       // the next tile's Wq
     // ---- R14: DensityMLP tail 32 -> 16 -> 1 in fp32 (hidden units 8 g .. 8 g + 7 per thread)

@@ -63,15 +63,24 @@ __device__ __forceinline__ float2 ln40_load(uint32_t tcol, float2 (*v)[4]) {
 #pragma unroll
   for (int i = 0; i < 5; ++i) tmem_ld8p(tcol + 8 * i, v[i]);
   umma::tmem_ld_wait();
-  float2 s = make_float2(0.f, 0.f), q2 = make_float2(0.f, 0.f);
+  // four independent accumulation chains per statistic: with two warps per scheduler the 4-cycle FMA latency of a single
+  // chain over 20 pairs would be exposed
+  float2 s[4], q2[4];
 #pragma unroll
-  for (int i = 0; i < 5; ++i)
+  for (int k = 0; k < 4; ++k) {
+    s[k] = v[0][k];
+    q2[k] = __fmul2_rn(v[0][k], v[0][k]);
+  }
+#pragma unroll
+  for (int i = 1; i < 5; ++i)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      s = __fadd2_rn(s, v[i][k]);
-      q2 = __ffma2_rn(v[i][k], v[i][k], q2);
+      s[k] = __fadd2_rn(s[k], v[i][k]);
+      q2[k] = __ffma2_rn(v[i][k], v[i][k], q2[k]);
     }
-  return make_float2(s.x + s.y, q2.x + q2.y);
+  const float2 st = __fadd2_rn(__fadd2_rn(s[0], s[1]), __fadd2_rn(s[2], s[3]));
+  const float2 qt = __fadd2_rn(__fadd2_rn(q2[0], q2[1]), __fadd2_rn(q2[2], q2[3]));
+  return make_float2(st.x + st.y, qt.x + qt.y);
 }
 __device__ __forceinline__ float2 ln2_stats(const float2* red, int r, float inv_n) {
   const float2 a0 = red[r], a1 = red[128 + r];
