@@ -226,8 +226,15 @@ static int tc_weights_build(const UfoWeightsDesc* d, TcWeights* t, cudaStream_t 
       pack_b(r2.data() + kR2WKv, kv.data(), 176, 88, 88, 176, 96, bf16);
       pack_b(r2.data() + kR2WQ, d->ray.q, 88, 88, 88, 96, 96, bf16);
       pack_b(r2.data() + kR2WMrg, d->ray.merge, 88, 88, 88, 96, 96, bf16);
-      pack_b(r2.data() + kR2WMl0a, d->ray.mlp0, 96, 176, 176, 96, 176, bf16);
-      pack_b(r2.data() + kR2WMl0b, d->ray.mlp0 + (size_t)96 * 176, 80, 176, 176, 80, 176, bf16);
+      // mlp.0 consumes [LN1 | x] (the kernel keeps the x operand where it is and writes LN1 below it): swap the K halves
+      std::vector<float> ml0((size_t)176 * 176);
+      for (int o = 0; o < 176; ++o)
+        for (int k = 0; k < 88; ++k) {
+          ml0[(size_t)o * 176 + k] = d->ray.mlp0[(size_t)o * 176 + 88 + k];
+          ml0[(size_t)o * 176 + 88 + k] = d->ray.mlp0[(size_t)o * 176 + k];
+        }
+      pack_b(r2.data() + kR2WMl0a, ml0.data(), 96, 176, 176, 96, 176, bf16);
+      pack_b(r2.data() + kR2WMl0b, ml0.data() + (size_t)96 * 176, 80, 176, 176, 80, 176, bf16);
       pack_b(r2.data() + kR2WMl2, d->ray.mlp2, 88, 176, 176, 96, 176, bf16);
       pack_b(r2.data() + kR2WDen, d->density.w0, 32, 88, 88, 32, 96, bf16, 0);
       pack_b(r2.data() + kR2WDen + 32 * 96 * 2, d->density.w0, 32, 88, 88, 32, 96, bf16, 1);

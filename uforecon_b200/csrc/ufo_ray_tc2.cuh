@@ -16,8 +16,8 @@
 //     issued as soon as the MMA that last read its slot has completed;
 //   * a thread owns one token row and one of two column halves.
 // TMEM columns (256): x [208,256) | k,v accumulator [0,176) | q accumulator [0,96) | Q' [96,144) | K^T.V per sequence
-// [0,96) [144,240) | message accumulator same | message operand [96,144) | merge accumulator [0,96) | [x | LN1] operand
-// [168,256) | mlp.0 accumulator, two passes [0,96) [0,80) | hidden operand [96,184) | mlp.2 accumulator [0,96) |
+// [0,96) [144,240) | message accumulator same | message operand [96,144) | merge accumulator [0,96) | [LN1 | x] operand
+// [168,256) (one sequence per tile: [164,252), x still in place from R0) | mlp.0 accumulator, two passes [0,96) [0,80) | hidden operand [96,184) | mlp.2 accumulator [0,96) |
 // r_hi [96,144) r_lo [144,192) | SRDF-head accumulator [0,32).
 #pragma once
 #include "ufo_view_tc2.cuh"
@@ -78,7 +78,9 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
   using namespace tc;
   constexpr uint32_t FMT = BF16 ? umma::kFmtBF16 : umma::kFmtF16;
   constexpr int NSEQ = 128 / SN;
-  constexpr uint32_t C_X = 208, C_QP = 96, C_M = 96, C_XL = 168, C_H1 = 96, C_RHI = 96, C_RLO = 144;      // operands
+  // [LN1 | x] operand of mlp.0: one sequence per tile (SN = 128) leaves the x operand of R0 untouched until mlp.0, so LN1 is
+  // written right below it and x is used in place; with two sequences the second K^T.V accumulator overwrites x and it is re-staged
+  constexpr uint32_t C_X = 208, C_QP = 96, C_M = 96, C_XL = (NSEQ == 1 ? 164 : 168), C_H1 = 96, C_RHI = 96, C_RLO = 144;      // operands
   constexpr uint32_t D_KV = 0, D_Q = 0, D_S0 = 0, D_S1 = 144, D_MRG = 0, D_ML0 = 0, D_ML2 = 0, D_DEN = 0;  // accumulators
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   uint8_t* const smem = tc_smem;
@@ -170,7 +172,7 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
 #pragma unroll
     for (int i = 0; i < 6; ++i) x_chunk(ir, 6 * g + i, xr[2 * i], xr[2 * i + 1]);
   };
-  // the loaded chunks as 16-bit operand chunks -> TMEM columns col0 + 4 c   (n_chunks: 12 for the QKV operand, 11 for [x | LN1])
+  // the loaded chunks as 16-bit operand chunks -> TMEM columns col0 + 4 c   (n_chunks: 12 for the QKV operand, 11 for [LN1 | x])
   auto x_store = [&](uint32_t col0, int n_chunks) {
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
@@ -344,10 +346,10 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
       issue_ts(D_MRG, C_M, b, 96, 96, 6, 0);
       umma::commit(bar);
     }
-    x_issue(in_row);                                             // x again, for the [x | LN1] operand: under the merge GEMM
+    if (NSEQ > 1) x_issue(in_row);                               // x again, for the [LN1 | x] operand: under the merge GEMM
     mma_wait();
     if (t == 0) load_piece(4);                                   // mlp.0 rows 96..175
-    // ---- R8: LayerNorm 1 -> second half of the concat operand [x | LN1] (chunks 11..21); x re-staged as chunks 0..10
+    // ---- R8: LayerNorm 1 -> first half of the concat operand [LN1 | x] (chunks 0..10; the weight image has the same K order)
     {
       auto r8 = [&](auto GGc) {
         constexpr int GG = decltype(GGc)::value;
@@ -357,7 +359,7 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
         for (int i = 0; i < NC; ++i) tmem_ld8p(tl + D_MRG + 8 * (C0 + i), v[i]);
         umma::tmem_ld_wait();
         red[GG * 128 + r] = ln_partial<NC>(v);
-        x_store(C_XL, 11);
+        if (NSEQ > 1) x_store(C_XL + 44, 11);
         umma::tc_fence_before();
         __syncthreads();
         const float2 st = ln2_stats(red, r, 1.f / 88.f);
@@ -366,7 +368,7 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
           const int c = C0 + i;
           float2 o[4];
           ln_apply(v[i], st, prm.n1w + 8 * c, prm.n1b + 8 * c, o);
-          umma::tmem_st4(tl + C_XL + 4 * (11 + c), pack2v<BF16>(o[0]), pack2v<BF16>(o[1]), pack2v<BF16>(o[2]), pack2v<BF16>(o[3]));
+          umma::tmem_st4(tl + C_XL + 4 * c, pack2v<BF16>(o[0]), pack2v<BF16>(o[1]), pack2v<BF16>(o[2]), pack2v<BF16>(o[3]));
         }
         umma::tmem_st_wait();
       };
@@ -374,7 +376,7 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     }
     umma::tc_fence_before();
     __syncthreads();
-    // ---- R9a: mlp.0 on [x | LN1]  (K = 176), output rows 0..95
+    // ---- R9a: mlp.0 on [LN1 | x]  (K = 176), output rows 0..95
     if (t == 0) {
       const uint32_t b = use_piece();
       umma::tc_fence_after();
@@ -408,9 +410,10 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
       issue_ts(D_ML0, C_XL, b, 80, 80, 11, 0);
       umma::commit(bar);
     }
+    x_issue(in_row);                                             // fp32 residual input of R12: two GEMMs ahead of its use
     mma_wait();
     if (t == 0) load_piece(6);                                   // SRDF head layer 0 (hi | lo)
-    // ---- R10b: ReLU -> hidden operand chunks 12..21 (over the dead [x | LN1] operand)
+    // ---- R10b: ReLU -> hidden operand chunks 12..21 (over the dead [LN1 | x] operand)
     {
       auto r10b = [&](auto GGc) {
         constexpr int GG = decltype(GGc)::value;
@@ -435,7 +438,6 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
       issue_ts(D_ML2, C_H1, b, 96, 96, 11, 0);
       umma::commit(bar);
     }
-    x_issue(in_row);                                             // fp32 residual input of this row: under the mlp.2 GEMM
     mma_wait();
     if (t == 0 && has_next) load_piece(0);                       // the next tile's Wkv
     // ---- R12: LayerNorm 2, residual in fp32 from the fp32 input, split hi/lo for the SRDF head
