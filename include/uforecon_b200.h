@@ -181,6 +181,12 @@ int ufo_render_rays_host(const UfoScene* scene, const UfoWeights* weights, int64
                          int32_t n_rays, const float* u_coarse_host, const float* u_fine_host,
                          int32_t mode, float* depth_z_host, float* rgb_host, void* stream);
 
+/* The library's temporaries (repacked feature maps of ufo_costvolume_stage*, staging of ufo_scene_create) come from the
+ * device's default stream-ordered memory pool, which the library keeps cached between calls (release threshold raised on
+ * first use; the default threshold of 0 re-maps gigabytes on every call).  ufo_trim_pool() synchronises the device and
+ * returns the cached memory to the driver. */
+int ufo_trim_pool(void);
+
 /* Number of kernel launches issued by this library since process start (bench.py's gpu_launches). */
 int64_t ufo_launch_count(void);
 

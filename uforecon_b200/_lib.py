@@ -84,6 +84,7 @@ EXPORTS = (
     "ufo_scene_create", "ufo_scene_destroy", "ufo_scene_device_bytes", "ufo_render_rays", "ufo_render_rays_host",
     "ufo_launch_count", "ufo_costvolume_stage", "ufo_costvolume_stage_rt", "ufo_debug_umma_selftest", "ufo_profile_begin", "ufo_profile_end",
     "ufo_tsdf_integrate", "ufo_feature_grid", "ufo_tsdf_mesh_begin", "ufo_tsdf_mesh_emit", "ufo_tsdf_mesh_destroy",
+    "ufo_trim_pool",
 )
 
 _lib = None

@@ -72,7 +72,25 @@ namespace {
 struct AsyncTemps {
   cudaStream_t st;
   std::vector<void*> ptrs;
-  explicit AsyncTemps(cudaStream_t s) : st(s) {}
+  explicit AsyncTemps(cudaStream_t s) : st(s) {
+    // The default pool hands freed memory back to the driver at the next synchronisation (release threshold 0), so every call
+    // re-mapped its gigabytes of temporaries: kernel 1 inside the reference cascade was SLOWER than the PyTorch loop it replaces
+    // at NV >= 5.  Keep the pool's memory cached, once per device (ufo_trim_pool() returns it).
+    static std::mutex mu;
+    static bool done[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) {
+      std::lock_guard<std::mutex> lk(mu);
+      if (!done[dev]) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+          unsigned long long keep = ~0ull;
+          cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        done[dev] = true;
+      }
+    }
+  }
   ~AsyncTemps() { for (void* p : ptrs) cudaFreeAsync(p, st); }
   int alloc(void** out, size_t bytes) {
     UFO_CUDA(cudaMallocAsync(out, bytes, st));
@@ -83,6 +101,16 @@ struct AsyncTemps {
 }  // namespace
 
 extern "C" int ufo_abi_version(void) { return UFO_ABI_VERSION; }
+extern "C" int ufo_trim_pool(void) {
+  if (int e = check_device()) return e;
+  int dev = 0;
+  UFO_CUDA(cudaGetDevice(&dev));
+  cudaMemPool_t pool;
+  UFO_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+  UFO_CUDA(cudaDeviceSynchronize());
+  UFO_CUDA(cudaMemPoolTrimTo(pool, 0));
+  return UFO_OK;
+}
 extern "C" const char* ufo_last_error(void) { return g_err; }
 extern "C" int64_t ufo_launch_count(void) { return (int64_t)g_launches.load(); }
 

@@ -523,17 +523,29 @@ __global__ void __launch_bounds__(256, UFO_GATHER_MINB) k_gather_tc(SceneDev sc,
         mma(c3[nt], h[0], w4f[0][nt][0], w4f[0][nt][1]);
         mma(c3[nt], h[1], w4f[1][nt][0], w4f[1][nt][1]);
       }
-      // token columns 56 + 8 nt + 2 t (two 16-bit values per store), the same for every view row of the point
+      // token columns 56..71, the same for every view row of the point: the four lanes of a quad hold 4 bytes each of a row's
+      // two 16-byte halves; they exchange them by shuffle and lane t writes the rows of views t, t+4, .. as 16-byte stores
+      // (4-byte stores, 4 NV per thread, cost 25 % of the kernel at NV = 10)
 #pragma unroll
       for (int hr = 0; hr < 2; ++hr) {
+        const uint32_t v0 = pk(c3[0][2 * hr], c3[0][2 * hr + 1]), v1 = pk(c3[1][2 * hr], c3[1][2 * hr + 1]);
+        const int qb = lane & ~3;
+        uint4 lo, hi;
+        lo.x = __shfl_sync(0xffffffffu, v0, qb);     lo.y = __shfl_sync(0xffffffffu, v0, qb + 1);
+        lo.z = __shfl_sync(0xffffffffu, v0, qb + 2); lo.w = __shfl_sync(0xffffffffu, v0, qb + 3);
+        hi.x = __shfl_sync(0xffffffffu, v1, qb);     hi.y = __shfl_sync(0xffffffffu, v1, qb + 1);
+        hi.z = __shfl_sync(0xffffffffu, v1, qb + 2); hi.w = __shfl_sync(0xffffffffu, v1, qb + 3);
         const long long p = p0 + (hr ? r1 : r0);
         if (p < P) {
           const size_t sl = (size_t)tc_slot(p, half);
 #pragma unroll
-          for (int nt = 0; nt < 2; ++nt) {
-            const uint32_t v = pk(c3[nt][2 * hr], c3[nt][2 * hr + 1]);
-#pragma unroll
-            for (int n = 0; n < NV; ++n) *reinterpret_cast<uint32_t*>(tok + (sl * NV + n) * kDView + 56 + 8 * nt + 2 * tq) = v;
+          for (int n0 = 0; n0 < NV; n0 += 4) {
+            const int n = n0 + tq;
+            if (n < NV) {
+              uint16_t* row = tok + (sl * NV + n) * kDView;
+              *reinterpret_cast<uint4*>(row + 56) = lo;
+              *reinterpret_cast<uint4*>(row + 64) = hi;
+            }
           }
         }
       }
