@@ -743,8 +743,11 @@ def roofline_entries(prof, args, n_rays, pk):
                         "rows it writes for the view stage) / live launch time; the limiter is L1 + issue, not HBM: see tap_gbs "
                         "(texel / voxel tap bytes pulled through L1) and the ncu utilisations")
             else:
-                work = tap
-                note = "no ncu capture for this configuration: achieved = texel / voxel tap bytes (L1 / L2 level), NOT DRAM bytes"
+                # no ncu capture at this view count / size: a lower bound of the launch's DRAM traffic that follows from the
+                # data layout alone - the 16-bit token rows, (r,g,b,mask) and direction rows it must write for the view stage
+                work = pts_pt * nv * (80 * 2 + 16 + 16)
+                note = ("no ncu capture for this configuration: achieved = the bytes the launch WRITES for the view stage (token, colour and "
+                        "direction rows; a lower bound of its DRAM traffic) / live launch time; the limiter is L1 + issue, see tap_gbs")
         if work is None:
             continue
         per_launch = work / cnt
