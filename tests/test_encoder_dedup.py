@@ -46,3 +46,22 @@ def test_dedup_encoder_is_bit_identical(nv):
         for k in ("depth", "prob_volume", "depth_values"):
             assert torch.equal(oa[st][k], ob[st][k]), (st, k)
     assert m.transmvsnet.feature.__class__.__name__ == "FeatureNet"     # restored
+
+
+@pytest.mark.parametrize("nv", [3, 4])
+def test_compact_match_features_are_the_reference_maps_stored_once(nv):
+    """N2 producer side: the compact pair maps equal every slot of the reference's redundant get_match_feat layout."""
+    from uforecon_b200.encoder import compact_match_features
+    from uforecon_b200.synthetic import expand_pair_maps
+    sd = checkpoint.synthetic_state_dict(0)
+    views = synthetic.UNFAVORABLE_VIEWS if nv == 3 else synthetic.TEN_VIEW_LIST[:nv]
+    batch = synthetic.make_batch(views, (160, 128))
+    m = reference_arm.load_model(nv, sd)
+    feats, _ = _encode(m, batch, True)
+    for i in range(len(feats)):
+        feats[i]["stage1"] = feats[i]["stage1"][0:1]                                  # model.py:782-783
+    with torch.no_grad():
+        ref = m.transmvsnet.get_match_feat(feats, cur_n_src_views=nv)[0]              # [1, NV, (NV-1)*32, h, w]  (model.py:785)
+        pairs = compact_match_features(m.transmvsnet, feats)
+    assert pairs is not None and tuple(pairs.shape) == (nv * (nv - 1) // 2, 32) + tuple(ref.shape[-2:])
+    assert torch.equal(expand_pair_maps(pairs, nv), ref)

@@ -145,6 +145,28 @@ def test_bf16_mode_is_retired():
     w.close()
 
 
+def test_fp16_mode_refuses_weights_outside_the_fp16_range():
+    """fp16 operand packing saturates at +-65504; a checkpoint with a larger GEMM weight would be clipped silently, so the
+    tensor-core mode refuses it (the fp32 mode renders it)."""
+    from uforecon_b200.renderer import HotPathWeights, Scene, render_rays
+    batch, scene, sd = make_case(synthetic.UNFAVORABLE_VIEWS, (96, 64))
+    sd = dict(sd)
+    k = next(n for n in sd if n.endswith("density_ray_transformer.layers.0.merge.weight"))
+    big = sd[k].clone()
+    big[0, 0] = 1.0e5
+    sd[k] = big
+    u_c, u_f = synthetic.sampler_uniforms(8, seed=5)
+    w = HotPathWeights(sd)
+    sc = Scene(batch, scene["source_imgs_feat"], scene["feature_volume"], scene["match_feature"])
+    with pytest.raises(UfoError, match="fp16 range"):
+        render_rays(sc, w, None, 8, u_c, u_f, UFO_MODE_TC_F16, ray_begin=0)
+    r = render_rays(sc, w, None, 8, u_c, u_f, UFO_MODE_FP32, ray_begin=0, want=("depth",))
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(r["depth"]).all())
+    sc.close()
+    w.close()
+
+
 @pytest.mark.parametrize("name", ["infer_nv3.npz", "infer_nv5.npz"])
 def test_tc_against_reference_goldens(name):
     """tensor-core mode against the outputs of the UNMODIFIED reference committed under tests/golden (tools/make_golden.py):

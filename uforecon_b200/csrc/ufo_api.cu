@@ -30,6 +30,7 @@ namespace {
 struct ProfRec { const char* name; cudaEvent_t e0, e1; };
 std::mutex g_prof_mu;
 std::vector<ProfRec> g_prof_recs;
+long long g_prof_epoch = 0;             // bumped whenever the record list is cleared: a handle from an earlier epoch is ignored
 std::vector<cudaEvent_t> g_prof_pool;   // recycled events
 cudaEvent_t prof_event() {
   if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
@@ -38,15 +39,19 @@ cudaEvent_t prof_event() {
   return e;
 }
 }  // namespace
-void prof_open(const char* name, cudaStream_t st) {
+// prof_open returns the index of ITS record and prof_close takes it back: with several host threads launching concurrently the
+// "last record" is not necessarily the caller's
+long long prof_open(const char* name, cudaStream_t st) {
   std::lock_guard<std::mutex> lock(g_prof_mu);
   ProfRec r{name, prof_event(), prof_event()};
   cudaEventRecord(r.e0, st);
   g_prof_recs.push_back(r);
+  return (g_prof_epoch << 32) | ((long long)g_prof_recs.size() - 1);
 }
-void prof_close(cudaStream_t st) {
+void prof_close(long long rec, cudaStream_t st) {
   std::lock_guard<std::mutex> lock(g_prof_mu);
-  if (!g_prof_recs.empty()) cudaEventRecord(g_prof_recs.back().e1, st);
+  const long long idx = rec & 0xffffffffll;
+  if (rec >= 0 && (rec >> 32) == g_prof_epoch && idx < (long long)g_prof_recs.size()) cudaEventRecord(g_prof_recs[(size_t)idx].e1, st);
 }
 }  // namespace ufo
 
@@ -156,11 +161,13 @@ static float back16(uint16_t u, bool bf16) {
 }
 // W [n_real][k_real] (row stride ldw) -> K-major chunk-major B operand image with n_pad rows, k_pad columns.
 // part 0: rounded value; part 1: rounded remainder (split precision).
+static float g_pack_max_abs = 0.f;   // running max |w| of the values pack_b has seen (read by tc_weights_build under its caller's lock-free, single-threaded build)
 static void pack_b(uint8_t* img, const float* W, int n_real, int k_real, int ldw, int n_pad, int k_pad, bool bf16, int part = 0) {
   uint16_t* o = reinterpret_cast<uint16_t*>(img);
   for (int n = 0; n < n_pad; ++n)
     for (int k = 0; k < k_pad; ++k) {
       const float v = (n < n_real && k < k_real) ? W[(size_t)n * ldw + k] : 0.f;
+      if (!(fabsf(v) <= g_pack_max_abs)) g_pack_max_abs = std::isfinite(v) ? fabsf(v) : INFINITY;
       uint16_t h = cvt16(v, bf16);
       if (part == 1) h = cvt16(v - back16(h, bf16), bf16);
       o[(size_t)(k / 8) * (n_pad * 8) + (size_t)n * 8 + (k % 8)] = h;
@@ -174,7 +181,11 @@ constexpr size_t kV2WQkv = 0, kV2WMrg = kV2WQkv + 240 * 80 * 2, kV2WMl0 = kV2WMr
 constexpr size_t kR2WKv = 0, kR2WQ = kR2WKv + 176 * 96 * 2, kR2WMrg = kR2WQ + 96 * 96 * 2, kR2WMl0a = kR2WMrg + 96 * 96 * 2,
                  kR2WMl0b = kR2WMl0a + 96 * 176 * 2, kR2WMl2 = kR2WMl0b + 80 * 176 * 2, kR2WDen = kR2WMl2 + 96 * 176 * 2,
                  kR2WEnd = kR2WDen + 2 * 32 * 96 * 2;
+static std::mutex g_tc_build_mu;
 static int tc_weights_build(const UfoWeightsDesc* d, TcWeights* t, cudaStream_t st) {
+  std::lock_guard<std::mutex> build_lock(g_tc_build_mu);
+  g_pack_max_abs = 0.f;
+  struct Record { TcWeights* t; ~Record() { t->max_abs_weight = g_pack_max_abs; } } record{t};
   for (int f = 0; f < 2; ++f) {
     const bool bf16 = (f == 0);
     std::vector<uint8_t> vi(tc::V_WEND, 0), ri(tc::RW_END, 0);
@@ -573,8 +584,12 @@ static int launch_linear(const float* X, int ldx, const float* W, float* Y, int 
   UFO_SMEM_ATTR((k_linear<K, N, R>), (int)smem);
   const long long tiles = (M + 63) / 64;
   const int grid = (int)(tiles < sms ? tiles : sms);
-  static char name[40] = "";
-  if (!name[0]) snprintf(name, sizeof(name), "k_linear<%d,%d>", K, N);
+  struct Name {            // built once, thread-safely (function-local static initialisation)
+    char s[40];
+    Name() { snprintf(s, sizeof(s), "k_linear<%d,%d>", K, N); }
+  };
+  static const Name name_holder;
+  const char* name = name_holder.s;
   UFO_KERNEL(name, st, k_linear<K, N, R><<<grid, 256, smem, st>>>(X, ldx, W, Y, ldy, M));
   return UFO_OK;
 }
@@ -819,6 +834,11 @@ extern "C" int ufo_render_rays(const UfoScene* sc, const UfoWeights* w, const in
     return fail(UFO_EINVAL, "ufo_render_rays: UFO_MODE_TC (bf16 operands) is retired - it misses the depth/colour tolerance at 1600x1216 "
                             "(p99 5.6e-3 of the interval, 46 dB); use UFO_MODE_TC_F16");
   if (mode != UFO_MODE_FP32 && mode != UFO_MODE_TC_F16) return fail(UFO_EINVAL, "ufo_render_rays: unknown mode %d", mode);
+  // fp16 operands saturate at +-65504: a checkpoint whose GEMM weights leave that range would be clipped silently - refuse instead
+  // (activations saturate too, cvt.rn.satfinite, but cannot be checked ahead of time; UFO_MODE_FP32 has no such limit)
+  if (mode == UFO_MODE_TC_F16 && !(w->tc.max_abs_weight <= 65504.f))
+    return fail(UFO_EINVAL, "ufo_render_rays: a transformer / head weight of magnitude %g is outside the fp16 range of UFO_MODE_TC_F16; use UFO_MODE_FP32",
+                (double)w->tc.max_abs_weight);
   if (!ray_idx && (ray_begin < 0 || ray_begin + n_rays > (int64_t)sc->d.H * sc->d.W))
     return fail(UFO_EINVAL, "ufo_render_rays: ray range [%lld,%lld) outside the %dx%d grid", (long long)ray_begin,
                 (long long)(ray_begin + n_rays), sc->d.H, sc->d.W);
@@ -1147,6 +1167,7 @@ extern "C" int ufo_profile_begin(void) {
   std::lock_guard<std::mutex> lock(g_prof_mu);
   for (auto& r : g_prof_recs) { g_prof_pool.push_back(r.e0); g_prof_pool.push_back(r.e1); }
   g_prof_recs.clear();
+  ++g_prof_epoch;
   g_prof_on.store(1);
   return UFO_OK;
 }
@@ -1169,6 +1190,7 @@ extern "C" int ufo_profile_end(UfoProfileEntry* out, int32_t cap, int32_t* n_out
     g_prof_pool.push_back(r.e1);
   }
   g_prof_recs.clear();
+  ++g_prof_epoch;
   int n = 0;
   for (auto& name : order) {
     if (n >= cap) break;

@@ -90,16 +90,16 @@ inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 // ProfScope brackets one launch with CUDA events on the launching stream.
 struct ProfState;
 extern std::atomic<int> g_prof_on;
-void prof_open(const char* name, cudaStream_t st);
-void prof_close(cudaStream_t st);
+long long prof_open(const char* name, cudaStream_t st);   // returns the record the matching prof_close completes
+void prof_close(long long rec, cudaStream_t st);
 struct ProfScope {
   cudaStream_t st;
-  bool on;
-  ProfScope(const char* name, cudaStream_t s) : st(s), on(g_prof_on.load(std::memory_order_relaxed) != 0) {
-    if (on) prof_open(name, st);
+  long long rec;
+  ProfScope(const char* name, cudaStream_t s) : st(s), rec(-1) {
+    if (g_prof_on.load(std::memory_order_relaxed) != 0) rec = prof_open(name, st);
   }
   ~ProfScope() {
-    if (on) prof_close(st);
+    if (rec >= 0) prof_close(rec, st);
   }
 };
 // Launch one kernel: optional event bracket, launch counter, launch-error check (returns on failure).

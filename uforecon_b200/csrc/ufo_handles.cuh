@@ -18,6 +18,7 @@ struct TcWeights {
   uint8_t* ray_img2[2] = {nullptr, nullptr};   // k_ray_tc2 pieces      (tc::R2W_END bytes, ufo_ray_tc2.cuh)
   ufo::ViewParams vp;
   ufo::RayParams rp;
+  float max_abs_weight = 0.f;                   // largest |w| among the GEMM weights packed as 16-bit operands
 };
 
 struct UfoWeights {

@@ -8,6 +8,12 @@ images as the first one, rotated by j along the batch axis - N^2 FPN passes for 
 manager the first call runs the FPN; the others return ``torch.roll`` of its outputs (new tensors, because
 ``FMT_with_pathway`` updates the per-view dicts in place, FMT.py:282-315).  Survey probe: the encoder is 4.7 / 16.1 / 64.6 s on
 8 CPU cores for N = 3 / 5 / 10 - the wall-clock floor of a depth map once the render is sub-second.
+
+``compact_match_features``  (N2, producer side) ``TransMVSNet.get_match_feat`` (TransMVSNet.py:341-374) stacks the cross-view
+maps of ``FMT_with_pathway.extract_cross_features`` into ``[B, NV, (NV-1)*32, h, w]``: every unordered pair's map appears
+twice, because ``FMT.forward(feat="cross")`` returns the same tensor for both images of a pair (FMT.py:197).
+This function returns the ``[NV(NV-1)/2, 32, h, w]`` tensor the FMT produced, without the redundant stack, for
+``Scene(..., pair_maps=...)`` / ``UfoSceneDesc.match_pairs`` (1.4 GB less at NV = 10, 1600x1216).
 """
 from __future__ import annotations
 
@@ -57,3 +63,23 @@ def dedup_feature_passes(transmvsnet: torch.nn.Module, check: bool = True):
         yield wrapped
     finally:
         transmvsnet.feature = orig
+
+
+def compact_match_features(transmvsnet: torch.nn.Module, features, check: bool = True) -> Optional[torch.Tensor]:
+    """The cross-view match maps with every view pair stored once: ``[NV(NV-1)/2, 32, h, w]``, pairs in the reference's
+    enumeration order ``(a, b) for a in range(NV-1) for b in range(a+1, NV)`` (model.py:273-276).
+
+    ``features`` is what ``TransMVSNet.forward`` returns first (one dict of FPN stages per view, stage 1 already cut to the first
+    rotation as ``extract_geometry`` does, model.py:782-783).  Returns ``None`` when the two tensors of the FMT differ (an encoder
+    whose cross attention is not symmetric): the caller then keeps the reference layout of ``get_match_feat``."""
+    out = transmvsnet.FMT_with_pathway.extract_cross_features(features)          # FMT.py:282-315
+    f0, f1 = out["aug_feat0s"][0], out["aug_feat1s"][0]                          # [B, nC2, 32, h, w] each
+    if check and not (f0 is f1 or torch.equal(f0, f1)):
+        return None
+    if f0.shape[0] != 1:
+        raise ValueError(f"expected batch 1 (stage-1 features of the first rotation), got {f0.shape[0]}")
+    nv = len(features)
+    n_pairs = nv * (nv - 1) // 2
+    # the FMT's cross output carries 2 nC2 maps (both attention directions, FMT.py:308-309); get_match_feat indexes the first nC2
+    # of them for BOTH views of a pair (TransMVSNet.py:362-366) - those are the maps the hot path samples
+    return f0[0, :n_pairs].contiguous()
