@@ -399,13 +399,12 @@ def run_b200(args):
     if world > 1:      # this rank's block of the uniforms as its own contiguous pinned host / device buffers
         u_c_hs = u_c_host[:, begin:begin + n_mine].contiguous().pin_memory()
         u_f_hs = u_f_host[:, begin:begin + n_mine].contiguous().pin_memory()
-        u_c_ds, u_f_ds = torch.empty_like(u_c_hs, device=dev), torch.empty_like(u_f_hs, device=dev)
 
     def step_e2e_sharded():
-        u_c_ds.copy_(u_c_hs, non_blocking=True)
-        u_f_ds.copy_(u_f_hs, non_blocking=True)
-        _lib.check(lib.ufo_render_rays(sc.handle, weights.handle, None, begin, n_mine, u_c_ds.data_ptr(), u_f_ds.data_ptr(), n_mine,
-                                       mode, C.byref(out), None, stream.cuda_stream))
+        # the same entry point as N = 1: uniforms of this rank's row block from pinned host memory, uploaded in column blocks on the
+        # library's copy stream under the render; the outputs stay on the device for the gather
+        _lib.check(lib.ufo_render_rays_host(sc.handle, weights.handle, begin, n_mine, u_c_hs.data_ptr(), u_f_hs.data_ptr(), mode,
+                                            out_depthz.data_ptr(), out_rgb.data_ptr(), stream.cuda_stream))
         got = ufodist.gather_depth_rgb(out_depthz[:n_mine], out_rgb[:n_mine], counts)
         if rank == 0:
             depth_host.copy_(got[0], non_blocking=True)
@@ -502,7 +501,7 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_h2d,
                     "d2h_bytes_per_step": e2e_d2h, "steps": k_e2e,
                     "api": ("ufo_render_rays_host (pinned host uniforms in, pinned host depth/rgb out)" if world == 1 else
-                            "per rank: pinned host uniforms of its row block in, ufo_render_rays, NCCL gather to rank 0, assembled depth/rgb to pinned host")},
+                            "per rank: ufo_render_rays_host on its row block (pinned host uniforms in, outputs kept on the device), NCCL gather to rank 0, assembled depth/rgb to pinned host")},
             "gpu_launches": int(launches),
             "accuracy": accuracy,
             "weak_scaling": weak,

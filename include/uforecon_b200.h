@@ -176,7 +176,8 @@ int ufo_render_rays(const UfoScene* scene, const UfoWeights* weights, const int6
 
 /* Same call with HOST buffers: copies uniforms host->device, renders, copies depth_z/rgb back and
  * synchronises the stream.  u_* are [64,n_rays] pinned or pageable host memory; depth_z [n_rays],
- * rgb [n_rays,3] host.  Rays are the range [ray_begin, ray_begin+n_rays). */
+ * rgb [n_rays,3] host (device pointers are accepted too: the copies use cudaMemcpyDefault - a rank of a row-sharded render
+ * keeps its block on the device for the NCCL gather).  Rays are the range [ray_begin, ray_begin+n_rays). */
 int ufo_render_rays_host(const UfoScene* scene, const UfoWeights* weights, int64_t ray_begin,
                          int32_t n_rays, const float* u_coarse_host, const float* u_fine_host,
                          int32_t mode, float* depth_z_host, float* rgb_host, void* stream);

@@ -920,8 +920,10 @@ extern "C" int ufo_render_rays_host(const UfoScene* sc, const UfoWeights* w, int
     ob.depth = o.depth + off;
     if (int e = ufo_render_rays(sc, w, nullptr, ray_begin + off, nb, u_c + off, u_f + off, n_rays, mode, &ob, nullptr, stream_)) return e;
   }
-  UFO_CUDA(cudaMemcpyAsync(depth_z_host, o.depth_z, sizeof(float) * n_rays, cudaMemcpyDeviceToHost, st));
-  UFO_CUDA(cudaMemcpyAsync(rgb_host, o.rgb, sizeof(float) * 3 * (size_t)n_rays, cudaMemcpyDeviceToHost, st));
+  // cudaMemcpyDefault: the destination is normally (pinned) host memory; a rank of a row-sharded render passes device buffers so
+  // that the NCCL gather can follow without a round trip through the host
+  UFO_CUDA(cudaMemcpyAsync(depth_z_host, o.depth_z, sizeof(float) * n_rays, cudaMemcpyDefault, st));
+  UFO_CUDA(cudaMemcpyAsync(rgb_host, o.rgb, sizeof(float) * 3 * (size_t)n_rays, cudaMemcpyDefault, st));
   UFO_CUDA(cudaStreamSynchronize(st));
   return UFO_OK;
 }
