@@ -68,19 +68,69 @@ __global__ void __launch_bounds__(256) k_costvol(const float* __restrict__ ref_c
     float sim[PPL];
 #pragma unroll
     for (int t = 0; t < PPL; ++t) sim[t] = 0.f;
-    const int lane0 = (threadIdx.x & 31) / LPP * LPP;           // first lane of this pixel's group
-#pragma unroll
-    for (int t = 0; t < PPL; ++t) {
-      // ---- lane l sets up the bilinear taps of ITS plane k = t*LPP + l once (round 1 evaluated the homography of every plane in
-      //      every lane: 186 warp instructions per lane and plane, the kernel was issue-bound on them); same arithmetic, same
-      //      roundings, so the result is bit-identical.  Shipped to the group: base texel offset, validity bits, four weights.
-      int s_off = 0;
-      unsigned s_ok = 0u;
-      float s_g00 = 0.f, s_g01 = 0.f, s_g10 = 0.f, s_g11 = 0.f;
-      if (l + t * LPP < D) {
-        const float d = dk[t];
+    if constexpr (LPP >= 4) {
+      const int lane0 = (threadIdx.x & 31) / LPP * LPP;           // first lane of this pixel's group
+  #pragma unroll
+      for (int t = 0; t < PPL; ++t) {
+        // ---- lane l sets up the bilinear taps of ITS plane k = t*LPP + l once (the first version evaluated the homography of every plane
+        //      in every lane: 186 warp instructions per lane and plane, issue-bound; stage 1 is 1.55 x faster this way); same arithmetic, same
+        //      roundings, so the result is bit-identical.  Shipped to the group: base texel offset, validity bits, four weights.
+        int s_off = 0;
+        unsigned s_ok = 0u;
+        float s_g00 = 0.f, s_g01 = 0.f, s_g10 = 0.f, s_g11 = 0.f;
+        if (l + t * LPP < D) {
+          const float d = dk[t];
+          const float X = __fadd_rn(__fmul_rn(rx, d), m.t[0]), Y = __fadd_rn(__fmul_rn(ry, d), m.t[1]), Z = __fadd_rn(__fmul_rn(rz, d), m.t[2]);
+          if (!(Z < 1e-6f)) {                                     // invalid -> grid -99 -> zero sample
+            const float gx = __fsub_rn(__fdiv_rn(__fdiv_rn(X, Z), (float)(w - 1) / 2.f), 1.f);
+            const float gy = __fsub_rn(__fdiv_rn(__fdiv_rn(Y, Z), (float)(h - 1) / 2.f), 1.f);
+            const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.f), 2.f), (float)(w - 1)), iy = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.f), 2.f), (float)(h - 1));
+            if ((ix > -1.f) && (ix < (float)w) && (iy > -1.f) && (iy < (float)h)) {
+              const float fx = floorf(ix), fy = floorf(iy);
+              const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+              const float wx1 = ix - fx, wx0 = (fx + 1.f) - ix, wy1 = iy - fy, wy0 = (fy + 1.f) - iy;
+              s_off = y0 * w + x0;                                // may be negative / past the row: only valid taps are read
+              s_ok = (x0 >= 0 && y0 >= 0 ? 1u : 0u) | (x1 < w && y0 >= 0 ? 2u : 0u) | (x0 >= 0 && y1 < h ? 4u : 0u) | (x1 < w && y1 < h ? 8u : 0u);
+              s_g00 = wx0 * wy0; s_g01 = wx1 * wy0; s_g10 = wx0 * wy1; s_g11 = wx1 * wy1;
+            }
+          }
+        }
+        for (int kk = 0; kk < LPP; ++kk) {
+          const int k = t * LPP + kk;
+          if (k >= D) break;                                        // uniform across the lane group
+          const int src_lane = lane0 + kk;
+          const int off = __shfl_sync(gmask, s_off, src_lane);
+          const unsigned ok = __shfl_sync(gmask, s_ok, src_lane);
+          float part = 0.f;
+          if (ok) {                                                 // uniform across the lane group
+            const float g00 = __shfl_sync(gmask, s_g00, src_lane), g01 = __shfl_sync(gmask, s_g01, src_lane);
+            const float g10 = __shfl_sync(gmask, s_g10, src_lane), g11 = __shfl_sync(gmask, s_g11, src_lane);
+            const float* tp = src + (long long)off * C;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok & 1u) { const float4 v = __ldg(reinterpret_cast<const float4*>(tp)); a.x = v.x * g00; a.y = v.y * g00; a.z = v.z * g00; a.w = v.w * g00; }
+            if (ok & 2u) { const float4 v = __ldg(reinterpret_cast<const float4*>(tp + C)); a.x = fmaf(v.x, g01, a.x); a.y = fmaf(v.y, g01, a.y); a.z = fmaf(v.z, g01, a.z); a.w = fmaf(v.w, g01, a.w); }
+            if (ok & 4u) { const float4 v = __ldg(reinterpret_cast<const float4*>(tp + (long long)w * C)); a.x = fmaf(v.x, g10, a.x); a.y = fmaf(v.y, g10, a.y); a.z = fmaf(v.z, g10, a.z); a.w = fmaf(v.w, g10, a.w); }
+            if (ok & 8u) { const float4 v = __ldg(reinterpret_cast<const float4*>(tp + (long long)(w + 1) * C)); a.x = fmaf(v.x, g11, a.x); a.y = fmaf(v.y, g11, a.y); a.z = fmaf(v.z, g11, a.z); a.w = fmaf(v.w, g11, a.w); }
+            part = a.x * rf.x + a.y * rf.y + a.z * rf.z + a.w * rf.w;
+          }
+  #pragma unroll
+          for (int o = LPP / 2; o > 0; o >>= 1) part += __shfl_xor_sync(gmask, part, o);
+          const float s = part / (float)C;                          // .mean(1)
+          if (kk == l) sim[t] = s;
+        }
+      }
+    } else {
+      // two lanes per pixel (stage 3, C = 8): sharing the set-up between two lanes costs more shuffles than it saves (measured +19 %)
+  #pragma unroll
+      for (int t = 0; t < PPL; ++t)
+      for (int kk = 0; kk < LPP; ++kk) {
+        const int k = t * LPP + kk;
+        if (k >= D) break;                                        // uniform across the lane group
+        // every lane of the group needs plane k's depth: broadcast from its owner lane kk
+        const float d = __shfl_sync(gmask, dk[t], (threadIdx.x & 31) / LPP * LPP + kk);
         const float X = __fadd_rn(__fmul_rn(rx, d), m.t[0]), Y = __fadd_rn(__fmul_rn(ry, d), m.t[1]), Z = __fadd_rn(__fmul_rn(rz, d), m.t[2]);
-        if (!(Z < 1e-6f)) {                                     // invalid -> grid -99 -> zero sample
+        float part = 0.f;
+        if (!(Z < 1e-6f)) {                                       // invalid -> grid -99 -> zero sample
           const float gx = __fsub_rn(__fdiv_rn(__fdiv_rn(X, Z), (float)(w - 1) / 2.f), 1.f);
           const float gy = __fsub_rn(__fdiv_rn(__fdiv_rn(Y, Z), (float)(h - 1) / 2.f), 1.f);
           const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.f), 2.f), (float)(w - 1)), iy = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.f), 2.f), (float)(h - 1));
@@ -88,31 +138,15 @@ __global__ void __launch_bounds__(256) k_costvol(const float* __restrict__ ref_c
             const float fx = floorf(ix), fy = floorf(iy);
             const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
             const float wx1 = ix - fx, wx0 = (fx + 1.f) - ix, wy1 = iy - fy, wy0 = (fy + 1.f) - iy;
-            s_off = y0 * w + x0;                                // may be negative / past the row: only valid taps are read
-            s_ok = (x0 >= 0 && y0 >= 0 ? 1u : 0u) | (x1 < w && y0 >= 0 ? 2u : 0u) | (x0 >= 0 && y1 < h ? 4u : 0u) | (x1 < w && y1 < h ? 8u : 0u);
-            s_g00 = wx0 * wy0; s_g01 = wx1 * wy0; s_g10 = wx0 * wy1; s_g11 = wx1 * wy1;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (x0 >= 0 && y0 >= 0) { const float4 v = __ldg(reinterpret_cast<const float4*>(src + ((size_t)y0 * w + x0) * C)); const float g = wx0 * wy0; a.x = v.x * g; a.y = v.y * g; a.z = v.z * g; a.w = v.w * g; }
+            if (x1 < w && y0 >= 0) { const float4 v = __ldg(reinterpret_cast<const float4*>(src + ((size_t)y0 * w + x1) * C)); const float g = wx1 * wy0; a.x = fmaf(v.x, g, a.x); a.y = fmaf(v.y, g, a.y); a.z = fmaf(v.z, g, a.z); a.w = fmaf(v.w, g, a.w); }
+            if (x0 >= 0 && y1 < h) { const float4 v = __ldg(reinterpret_cast<const float4*>(src + ((size_t)y1 * w + x0) * C)); const float g = wx0 * wy1; a.x = fmaf(v.x, g, a.x); a.y = fmaf(v.y, g, a.y); a.z = fmaf(v.z, g, a.z); a.w = fmaf(v.w, g, a.w); }
+            if (x1 < w && y1 < h) { const float4 v = __ldg(reinterpret_cast<const float4*>(src + ((size_t)y1 * w + x1) * C)); const float g = wx1 * wy1; a.x = fmaf(v.x, g, a.x); a.y = fmaf(v.y, g, a.y); a.z = fmaf(v.z, g, a.z); a.w = fmaf(v.w, g, a.w); }
+            part = a.x * rf.x + a.y * rf.y + a.z * rf.z + a.w * rf.w;
           }
         }
-      }
-      for (int kk = 0; kk < LPP; ++kk) {
-        const int k = t * LPP + kk;
-        if (k >= D) break;                                        // uniform across the lane group
-        const int src_lane = lane0 + kk;
-        const int off = __shfl_sync(gmask, s_off, src_lane);
-        const unsigned ok = __shfl_sync(gmask, s_ok, src_lane);
-        float part = 0.f;
-        if (ok) {                                                 // uniform across the lane group
-          const float g00 = __shfl_sync(gmask, s_g00, src_lane), g01 = __shfl_sync(gmask, s_g01, src_lane);
-          const float g10 = __shfl_sync(gmask, s_g10, src_lane), g11 = __shfl_sync(gmask, s_g11, src_lane);
-          const float* tp = src + (long long)off * C;
-          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ok & 1u) { const float4 v = __ldg(reinterpret_cast<const float4*>(tp)); a.x = v.x * g00; a.y = v.y * g00; a.z = v.z * g00; a.w = v.w * g00; }
-          if (ok & 2u) { const float4 v = __ldg(reinterpret_cast<const float4*>(tp + C)); a.x = fmaf(v.x, g01, a.x); a.y = fmaf(v.y, g01, a.y); a.z = fmaf(v.z, g01, a.z); a.w = fmaf(v.w, g01, a.w); }
-          if (ok & 4u) { const float4 v = __ldg(reinterpret_cast<const float4*>(tp + (long long)w * C)); a.x = fmaf(v.x, g10, a.x); a.y = fmaf(v.y, g10, a.y); a.z = fmaf(v.z, g10, a.z); a.w = fmaf(v.w, g10, a.w); }
-          if (ok & 8u) { const float4 v = __ldg(reinterpret_cast<const float4*>(tp + (long long)(w + 1) * C)); a.x = fmaf(v.x, g11, a.x); a.y = fmaf(v.y, g11, a.y); a.z = fmaf(v.z, g11, a.z); a.w = fmaf(v.w, g11, a.w); }
-          part = a.x * rf.x + a.y * rf.y + a.z * rf.z + a.w * rf.w;
-        }
-#pragma unroll
+  #pragma unroll
         for (int o = LPP / 2; o > 0; o >>= 1) part += __shfl_xor_sync(gmask, part, o);
         const float s = part / (float)C;                          // .mean(1)
         if (kk == l) sim[t] = s;
