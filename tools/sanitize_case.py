@@ -14,7 +14,7 @@ from uforecon_b200.renderer import HotPathWeights, Scene, render_rays  # noqa: E
 
 def main():
     nv = int(sys.argv[1]) if len(sys.argv) > 1 else 3
-    mode = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    mode = int(sys.argv[2]) if len(sys.argv) > 2 else 2      # UFO_MODE_TC_F16 (0 = fp32; 1 = bf16 is retired)
     views = synthetic.UNFAVORABLE_VIEWS if nv == 3 else synthetic.TEN_VIEW_LIST[:nv]
     batch, scene, sd = make_case(views, (96, 64))
     n = 67

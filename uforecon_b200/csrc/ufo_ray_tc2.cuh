@@ -147,10 +147,17 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     load_piece(0);
     load_piece(1);
   }
+  // Input row of this thread's token in a tile.  With sorted samples it goes through the sort permutation: that byte load is issued
+  // by inline asm at the program position of the call (one tile ahead, see below) - as plain C++ the compiler sank it next to its
+  // first use, and 10 % of the kernel's stall samples waited on the perm -> address -> x dependency chain.
   auto in_row_of = [&](long long tile) -> long long {
     const long long prow = tile * 128 + r;
     if (prow >= P) return -1;
-    return (SN == kNC) ? tc_slot(prow, 0) : tile * 128 + (perm ? (long long)perm[prow] : (long long)r);
+    if (SN == kNC) return tc_slot(prow, 0);
+    if (perm == nullptr) return tile * 128 + r;
+    unsigned pv;
+    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(pv) : "l"(perm + prow));
+    return tile * 128 + (long long)pv;
   };
   // chunk c (8 channels) of this row's fp32 input: view-stage output (c < 10) or order encoding (c == 10)
   auto x_chunk = [&](long long ir, int c, float4& a, float4& b) {
@@ -182,12 +189,13 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
                        umma::pack2<BF16>(xr[2 * i + 1].x, xr[2 * i + 1].y), umma::pack2<BF16>(xr[2 * i + 1].z, xr[2 * i + 1].w));
     }
   };
-  if ((long long)blockIdx.x < n_tiles) x_issue(in_row_of(blockIdx.x));
+  long long in_row_cur = (long long)blockIdx.x < n_tiles ? in_row_of(blockIdx.x) : -1;
+  if ((long long)blockIdx.x < n_tiles) x_issue(in_row_cur);
 
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const long long prow = tile * 128 + r;           // this thread's token: ray prow / SN, sorted sample prow % SN
     const bool row_ok = prow < P;
-    const long long in_row = in_row_of(tile);
+    const long long in_row = in_row_cur;             // looked up one tile ahead (in_row_nx of the previous iteration)
     const bool has_next = tile + (long long)gridDim.x < n_tiles;
     const long long in_row_nx = has_next ? in_row_of(tile + gridDim.x) : -1;      // its perm lookup completes long before it is used
     // ---- R0: x = [view-stage token 0 output | order encoding | 0] -> 16-bit A operand in TMEM (chunks 6 g .. 6 g + 5)
@@ -493,6 +501,7 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
       umma::commit(bar);
     }
     if (has_next) x_issue(in_row_nx);                            // the next tile's x: under the SRDF-head GEMM and its tail
+    in_row_cur = in_row_nx;
     mma_wait();
     if (t == 0 && has_next) load_piece(1);                       // the next tile's Wq
     // ---- R14: DensityMLP tail 32 -> 16 -> 1 in fp32 (hidden units 8 g .. 8 g + 7 per thread)
