@@ -27,8 +27,11 @@ struct WarpMats {           // per (rotation, source view): rot (3x3) and trans 
   float r[9], t[3];
 };
 
+#ifndef UFO_COSTVOL_MINB
+#define UFO_COSTVOL_MINB 3      // <= 80 registers: 3 blocks per SM (measured 1.59 / 2.85 / 1.63 ms vs 1.68 / 3.34 / 1.67 ms unbounded, NV=3 at 1600x1216)
+#endif
 template <int C, int D, bool kComputeVW>
-__global__ void __launch_bounds__(256) k_costvol(const float* __restrict__ ref_cl /*[N][h][w][C]*/,
+__global__ void __launch_bounds__(256, UFO_COSTVOL_MINB) k_costvol(const float* __restrict__ ref_cl /*[N][h][w][C]*/,
                                                 const float* const* __restrict__ src_cl /*[V-1] x [N][h][w][C]*/,
                                                 const WarpMats* __restrict__ mats /*[N][V-1]*/,
                                                 const float* __restrict__ hyp /*[N][D][h][w]*/,
