@@ -26,7 +26,7 @@ TAPS = ("z_coarse", "weight_coarse", "srdf_coarse", "z_fine", "sim8", "vol24", "
 BOUNDS = {UFO_MODE_TC_F16: (8e-4, 2e-3, 2e-3, 3e-3)}
 
 
-@pytest.fixture(scope="module", params=[3, 5, 2, 10])
+@pytest.fixture(scope="module", params=[3, 5, 2, 10, 8])
 def tc_case(request):
     from uforecon_b200.renderer import HotPathWeights, Scene, render_rays
     nv = request.param

@@ -22,15 +22,16 @@ static int launch_tc_pass(const UfoScene* sc, const UfoWeights* w, int R, int ha
   }
   UFO_KERNEL("k_gather_tc", st, k_gather_tc<NV, BF16><<<cdiv(P, 256), 256, gather_tc_smem<NV>(), st>>>(sc->d, ws.rayinfo, z, R, half, w->freqs, w->phases, w->pre_sim,
                                                                                   ws.tok, ws.rgbm, ws.dirs, want_sim8 ? ws.sim8 : nullptr));
-  // Generation 2 (two tiles in flight, points aligned to warps) wins wherever its row utilisation is decent: measured on a B200
-  // at 1600x1216, ms per depth map in the view stage: NV=3 243 vs 360, NV=5 395 vs 611.  At NV=10 (11 tokens per point) only 2
-  // points fit a warp (22 of 32 rows) and generation 1, which packs 11 points into a tile, is 10 % faster (1470 vs 1640).
+  // Generation 2 (two tiles in flight; the token rows of a point aligned to a warp, or to a warp pair where a single warp would leave
+  // > 5 % more rows idle: NV = 6, 8, 10) is the default for every view count.  Measured on a B200 at 1600x1216, ms per depth map in
+  // the view stage, generation 2 vs generation 1 (lock step): NV=3 243 vs 360, NV=5 395 vs 611, NV=10 1372 vs 1467 (with warp-aligned
+  // points only 22 of 32 rows were in use at NV=10 and generation 2 lost: 1640).  UFO_VIEW_KERNEL=1 selects generation 1.
   static const int view_env = getenv("UFO_VIEW_KERNEL") ? atoi(getenv("UFO_VIEW_KERNEL")) : 0;
-  const int view_gen = view_env ? view_env : (NV >= 10 ? 1 : 2);
+  const int view_gen = view_env ? view_env : 2;
   static_assert(tc::V2_WEND == 141312, "k_view_tc2 weight image size (mirrored in ufo_api.cu)");
   if (view_gen == 2) {     // two tiles in flight per CTA (ufo_view_tc2.cuh)
     UFO_SMEM_ATTR((k_view_tc2<NV, BF16>), (int)tc::V2_SMEM);
-    constexpr int PPT = 4 * (32 / (NV + 1));
+    constexpr int PPT = tc::view2_points_per_tile(NV);
     const long long tiles = (P + PPT - 1) / PPT;
     const long long pairs = (tiles + 1) / 2;
     const int grid = (int)(pairs < sms ? pairs : sms);

@@ -13,7 +13,8 @@
 //     by its row owner straight into TMEM (tcgen05.st) and consumed as the A operand of a TS-form tcgen05.mma - no
 //     shared-memory staging, no fence.proxy.async, half the shared-memory bandwidth per MMA;
 //   * the per-point attention exchanges K'/V' between the L = NV+1 token rows of a point inside one warp (points are
-//     aligned to warps: floor(32/L) points per warp) through a 2.5 KB per-warp buffer, in fp32, one head at a time -
+//     aligned to warps: floor(32/L) points per warp; to warp pairs with a 64-thread named barrier for L = 7, 9, 11, where a
+//     single warp would leave up to 10 of 32 rows idle) through a 2.5 KB per-warp buffer, in fp32, one head at a time -
 //     no 16-bit staging tile, no CTA-wide barrier between the elu phase and the attention (warp shuffles were
 //     measured first: 2560 SHFL per tile, 19 % of the stall samples on the MIO queue);
 //   * the weights (138 KB) stay resident and are shared by both halves; the only activation operand in shared memory
@@ -53,6 +54,15 @@ __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Rows over which the L = NV+1 token rows of a point may spread: one warp (32 TMEM lanes) when that wastes < 5 % more rows than
+// a warp pair, else two warps (64 rows) - L = 7, 9, 11 (NV = 6, 8, 10) leave 4, 5, 10 of 32 rows idle in a single warp, 1, 1, 9 of 64 in
+// a pair.  The K'/V' exchange of the attention is then synchronised by a 64-thread named barrier instead of __syncwarp.
+__host__ __device__ constexpr int view2_group_rows(int nv) {
+  const int L = nv + 1;
+  return ((64 / L) * L * 32 - (32 / L) * L * 64) * 20 > 64 * 32 ? 64 : 32;      // util64 - util32 > 0.05
+}
+__host__ __device__ constexpr int view2_points_per_tile(int nv) { return (128 / view2_group_rows(nv)) * (view2_group_rows(nv) / (nv + 1)); }
 
 #define UFO_G2_DISPATCH(fn)     \
   if (g == 0) fn(IC<0>{});      \
@@ -96,7 +106,8 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
            const float4* __restrict__ rgbm, const float4* __restrict__ dirs, int P, int half, float* __restrict__ vout0,
            float4* __restrict__ radiance) {
   using namespace tc;
-  constexpr int L = NV + 1, PPW = 32 / L, PPT = 4 * PPW, RPW = PPW * L;   // points per warp / tile, rows in use per warp
+  constexpr int L = NV + 1, GR = tc::view2_group_rows(NV), PPW = GR / L, PPT = (128 / GR) * PPW, RPW = PPW * L;   // rows of an exchange
+                                                                        // group (warp or warp pair), points per group / tile, rows in use per group
   static_assert(PPT * NV <= 112, "colour staging too small");
   constexpr uint32_t FMT = BF16 ? umma::kFmtBF16 : umma::kFmtF16;
   constexpr uint32_t D_QKV = 0, D_RAD = 240, D_MRG = 144, D_ML0 = 80, D_ML2 = 80;
@@ -104,9 +115,10 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
   uint8_t* const smem = tc_smem;
   const int tid = threadIdx.x, hf = tid >> 8, t = tid & 255, lane = tid & 31, wl = t >> 5;
   const int q = wl & 3, g = wl >> 2, r = q * 32 + lane;
-  const int pl = q * PPW + lane / L, l = lane % L;
-  const bool row_ok = lane < RPW;
-  const int sl0 = (lane / L) * L;                       // first lane of this row's point
+  const int gr = r % GR;                                // row inside its exchange group
+  const int pl = (r / GR) * PPW + gr / L, l = gr % L;
+  const bool row_ok = gr < RPW;
+  const int sl0 = (gr / L) * L;                         // first group row of this row's point
   uint8_t* const hs = smem + V2_HALF + hf * V2H_SIZE;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + V2_BAR) + hf;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + V2_BAR + 32);
@@ -127,7 +139,7 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
   for (int i = tid; i < 2 * 1280; i += 512) {
     const int hb = i / 1280, j = i - hb * 1280;          // half, piece
     const int rr = j & 127, c = j >> 7;
-    const int ln = rr & 31;
+    const int ln = rr % GR;
     float v[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = (ln < RPW && (ln % L) == 0) ? prm.vtok[c * 8 + k] : 0.f;
@@ -154,9 +166,9 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
     for (int k = 0; k < 5; ++k) {
       const int i = t + k * 256;
       const int rr = i & 127, c = i >> 7;
-      const int ln = rr & 31;
+      const int ln = rr % GR;
       const int ll = ln % L;
-      const int p = pbase + (rr >> 5) * PPW + ln / L;
+      const int p = pbase + (rr / GR) * PPW + ln / L;
       if (ln < RPW && ll > 0 && p < P)
         cp_async16(x_base + c * kChunk + rr * 16,
                    tok + (size_t)slot_of(p) * (NV * kDView) + (ll - 1) * kDView + c * 8);
@@ -177,7 +189,13 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
   };
   int tile = 2 * blockIdx.x + hf;
   if (tile < n_tiles) load_tokens(tile);
-  float4* const xw = reinterpret_cast<float4*>(hs + V2H_XCH + wl * 2560);   // this warp's exchange buffer [32][5] float4
+  // exchange buffer of this (column group, row group): [GR rows][5] float4; same 20 KB per half for either group size
+  float4* const xw = reinterpret_cast<float4*>(hs + V2H_XCH + (g * (128 / GR) + r / GR) * (GR * 80));
+  const uint32_t xbar_id = 3 + hf * 4 + g * 2 + (q >> 1);                    // named barrier of a warp pair (GR == 64), ids 3..10
+  auto group_sync = [&]() {
+    if (GR == 32) __syncwarp();
+    else umma::bar_sync(xbar_id, 64);
+  };
 
   for (; tile < n_tiles; tile += tstep) {
     const int pbase = tile * PPT;
@@ -236,20 +254,20 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           // this row's K' | V of the head -> the warp's exchange buffer (80 B rows: conflict-free 16-byte stores)
-          __syncwarp();                                         // the previous head's readers are done
-          xw[lane * 5 + 0] = make_float4(k2[5 * hh].x, k2[5 * hh].y, k2[5 * hh + 1].x, k2[5 * hh + 1].y);
-          xw[lane * 5 + 1] = make_float4(k2[5 * hh + 2].x, k2[5 * hh + 2].y, k2[5 * hh + 3].x, k2[5 * hh + 3].y);
-          xw[lane * 5 + 2] = make_float4(k2[5 * hh + 4].x, k2[5 * hh + 4].y, vf[10 * hh], vf[10 * hh + 1]);
-          xw[lane * 5 + 3] = make_float4(vf[10 * hh + 2], vf[10 * hh + 3], vf[10 * hh + 4], vf[10 * hh + 5]);
-          xw[lane * 5 + 4] = make_float4(vf[10 * hh + 6], vf[10 * hh + 7], vf[10 * hh + 8], vf[10 * hh + 9]);
-          __syncwarp();
+          group_sync();                                         // the previous head's readers are done
+          xw[gr * 5 + 0] = make_float4(k2[5 * hh].x, k2[5 * hh].y, k2[5 * hh + 1].x, k2[5 * hh + 1].y);
+          xw[gr * 5 + 1] = make_float4(k2[5 * hh + 2].x, k2[5 * hh + 2].y, k2[5 * hh + 3].x, k2[5 * hh + 3].y);
+          xw[gr * 5 + 2] = make_float4(k2[5 * hh + 4].x, k2[5 * hh + 4].y, vf[10 * hh], vf[10 * hh + 1]);
+          xw[gr * 5 + 3] = make_float4(vf[10 * hh + 2], vf[10 * hh + 3], vf[10 * hh + 4], vf[10 * hh + 5]);
+          xw[gr * 5 + 4] = make_float4(vf[10 * hh + 6], vf[10 * hh + 7], vf[10 * hh + 8], vf[10 * hh + 9]);
+          group_sync();
           float2 msg[5];
 #pragma unroll
           for (int b = 0; b < 5; ++b) msg[b] = make_float2(0.f, 0.f);
           float den = 0.f;
 #pragma unroll
           for (int s = 0; s < L; ++s) {
-            const float4* src = xw + ((sl0 + s) & 31) * 5;     // the same address for the L rows of a point: broadcast
+            const float4* src = xw + ((sl0 + s) & (GR - 1)) * 5;   // the same address for the L rows of a point: broadcast
             const float4 a0 = src[0], a1 = src[1], a2 = src[2], a3 = src[3], a4 = src[4];
             float2 acc = __fmul2_rn(q2[5 * hh], make_float2(a0.x, a0.y));
             acc = __ffma2_rn(q2[5 * hh + 1], make_float2(a0.z, a0.w), acc);
@@ -450,7 +468,7 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
     umma::bar_sync(bar_id, 256);
     if (t < PPT && pbase + t < P) {
       const size_t p = (size_t)slot_of(pbase + t);
-      const int rr0 = (t / PPW) * 32 + (t % PPW) * L + 1;        // row of (point t, view 0)
+      const int rr0 = (t / PPW) * GR + (t % PPW) * L + 1;        // row of (point t, view 0)
       float om[NV];
       float4 col[NV];
       float mx = -INFINITY;
