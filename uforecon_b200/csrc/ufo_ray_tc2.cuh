@@ -89,7 +89,8 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + R2_BAR + 32);
   float2* red = reinterpret_cast<float2*>(smem + R2_SCR);
   float* part_s = reinterpret_cast<float*>(smem + R2_SCR);
-  const int t = threadIdx.x, lane = t & 31, wl = t >> 5;
+  // warp index through a shuffle: provably warp-uniform, so that TMEM addresses and the column-group dispatch run on the uniform datapath
+  const int t = threadIdx.x, lane = t & 31, wl = __shfl_sync(0xffffffffu, t >> 5, 0);
   const int q = wl & 3, g = wl >> 2, r = q * 32 + lane;
   const long long n_tiles = (P + 127) / 128;
 
@@ -109,26 +110,49 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
   umma::tc_fence_before();
   __syncthreads();
   umma::tc_fence_after();
-  const uint32_t tm = *tmem_slot;
+  const uint32_t tm = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const uint32_t tl = tm + ((uint32_t)(q * 32) << 16);
   const uint32_t sm_base = umma::smem_u32(smem);
   uint32_t ph = 0;
 
-  // ---- weight streaming: piece j of the running sequence goes to slot (pc & 1); all by thread 0
-  uint32_t pc_load = 0, pc_use = 0, fph0 = 0, fph1 = 0;
+  // ---- weight streaming: piece j of the running sequence goes to slot (pc & 1); the copies and the waits are thread 0's, the
+  //      BOOKKEEPING (piece counters, mbarrier phases) is kept by every thread at uniform program points: slot addresses and barrier
+  //      parities are then warp-uniform values and the issuing thread's descriptors are built on the uniform datapath.  (Kept by thread 0
+  //      alone they were thread-private data: every tcgen05.mma / cp.async.bulk was wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop,
+  //      14 dependent instructions per MMA in the one thread the other 255 wait for.)
+#ifdef UFO_RAY_LOAD_T0
+  constexpr int kLoadThread = 0;
+#else
+  constexpr int kLoadThread = 128;
+#endif
+  uint32_t pc_load = 0, pc_use = 0, fph = 0;                  // fph bit s: phase parity of slot s
   auto load_piece = [&](int j) {
     const uint32_t off[7] = {R2W_KV, R2W_Q, R2W_MRG, R2W_ML0A, R2W_ML0B, R2W_ML2, R2W_DEN};
     const uint32_t len[7] = {176 * 96 * 2, 96 * 96 * 2, 96 * 96 * 2, 96 * 176 * 2, 80 * 176 * 2, 96 * 176 * 2, 2 * 32 * 96 * 2};
     const uint32_t s = pc_load & 1;
-    bulk_load(smem + R2_SLOT + s * R2_SLOT_BYTES, wimg + off[j], len[j], full + s);
     ++pc_load;
+    // the copies are issued by a thread of warp 4: the g = 1 warps own 5 of the 11 chunks of a row, so they reach the end of an
+    // epilogue first, and warp 0 (which issues the MMAs) starts its epilogue without this detour (-DUFO_RAY_LOAD_T0: thread 0)
+    if (t == kLoadThread) bulk_load(smem + R2_SLOT + s * R2_SLOT_BYTES, wimg + off[j], len[j], full + s);
   };
-  // issuer: wait until the piece about to be used has landed; returns its slot's shared-memory address
+  // every thread: slot and parity of the piece about to be used; thread 0 waits until it has landed (use_wait) before it issues
+  uint32_t use_s = 0, use_par = 0;
   auto use_piece = [&]() -> uint32_t {
-    const uint32_t s = pc_use & 1;
-    if (s == 0) { umma::mbar_wait(full, fph0); fph0 ^= 1; } else { umma::mbar_wait(full + 1, fph1); fph1 ^= 1; }
+    use_s = pc_use & 1;
+    use_par = (fph >> use_s) & 1u;
+    fph ^= 1u << use_s;
     ++pc_use;
-    return sm_base + R2_SLOT + s * R2_SLOT_BYTES;
+    return sm_base + R2_SLOT + use_s * R2_SLOT_BYTES;
+  };
+  auto use_wait = [&]() { umma::mbar_wait(full + use_s, use_par); };
+  // the two warps that share the token rows 32 q .. 32 q + 31 (column halves g = 0, 1): a 64-thread named barrier where only they
+  // exchange data (LayerNorm / SRDF partials); -DUFO_RAY_CTA_SYNC restores the CTA-wide barrier
+  auto pair_sync = [&]() {
+#ifdef UFO_RAY_CTA_SYNC
+    __syncthreads();
+#else
+    umma::bar_sync(1 + q, 64);
+#endif
   };
   auto mma_wait = [&]() {
     umma::mbar_wait(bar, ph);
@@ -143,7 +167,7 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
       umma::mma_f16_ts(tm + d_col, tm + a_col + 8 * ks, umma::make_smem_desc(b_addr + 2 * ks * lbo, lbo, 128u), idesc, ks > 0 ? 1u : acc_first);
   };
 
-  if (t == 0 && (long long)blockIdx.x < n_tiles) {
+  if ((long long)blockIdx.x < n_tiles) {
     load_piece(0);
     load_piece(1);
   }
@@ -204,14 +228,15 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     umma::tc_fence_before();
     __syncthreads();
     // ---- R1a: k | v = x . Wkv^T
+    const uint32_t b1 = use_piece();
     if (t == 0) {
-      const uint32_t b = use_piece();
+      use_wait();
       umma::tc_fence_after();
-      issue_ts(D_KV, C_X, b, 176, 176, 6, 0);
+      issue_ts(D_KV, C_X, b1, 176, 176, 6, 0);
       umma::commit(bar);
     }
     mma_wait();
-    if (t == 0) load_piece(2);                                   // merge weights -> the slot Wkv leaves
+    load_piece(2);                                   // merge weights -> the slot Wkv leaves
     // ---- R2a: K' = elu(k)+1, V' = v -> MN-major operand tiles in shared memory   (linear_attention.py:36-41)
     {
       auto r2a = [&](auto GGc) {
@@ -238,14 +263,15 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     umma::tc_fence_before();
     __syncthreads();
     // ---- R1b: q = x . Wq^T   (the k | v accumulator is consumed)
+    const uint32_t b2 = use_piece();
     if (t == 0) {
-      const uint32_t b = use_piece();
+      use_wait();
       umma::tc_fence_after();
-      issue_ts(D_Q, C_X, b, 96, 96, 6, 0);
+      issue_ts(D_Q, C_X, b2, 96, 96, 6, 0);
       umma::commit(bar);
     }
     mma_wait();
-    if (t == 0) load_piece(3);                                   // mlp.0 rows 0..95
+    load_piece(3);                                   // mlp.0 rows 0..95
     // ---- R2b: Q' = elu(q)+1 -> A operand of the message GEMM (chunk 11 = 0)
     {
       auto r2b = [&](auto GGc) {
@@ -348,15 +374,16 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     umma::tc_fence_before();
     __syncthreads();
     // ---- R7: merge
+    const uint32_t b3 = use_piece();
     if (t == 0) {
-      const uint32_t b = use_piece();
+      use_wait();
       umma::tc_fence_after();
-      issue_ts(D_MRG, C_M, b, 96, 96, 6, 0);
+      issue_ts(D_MRG, C_M, b3, 96, 96, 6, 0);
       umma::commit(bar);
     }
     if (NSEQ > 1) x_issue(in_row);                               // x again, for the [LN1 | x] operand: under the merge GEMM
     mma_wait();
-    if (t == 0) load_piece(4);                                   // mlp.0 rows 96..175
+    load_piece(4);                                   // mlp.0 rows 96..175
     // ---- R8: LayerNorm 1 -> first half of the concat operand [LN1 | x] (chunks 0..10; the weight image has the same K order)
     {
       auto r8 = [&](auto GGc) {
@@ -369,7 +396,7 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
         red[GG * 128 + r] = ln_partial<NC>(v);
         if (NSEQ > 1) x_store(C_XL + 44, 11);
         umma::tc_fence_before();
-        __syncthreads();
+        pair_sync();                                               // the partials of a row come from the warps q and q + 4 only
         const float2 st = ln2_stats(red, r, 1.f / 88.f);
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
@@ -385,14 +412,15 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     umma::tc_fence_before();
     __syncthreads();
     // ---- R9a: mlp.0 on [LN1 | x]  (K = 176), output rows 0..95
+    const uint32_t b4 = use_piece();
     if (t == 0) {
-      const uint32_t b = use_piece();
+      use_wait();
       umma::tc_fence_after();
-      issue_ts(D_ML0, C_XL, b, 96, 96, 11, 0);
+      issue_ts(D_ML0, C_XL, b4, 96, 96, 11, 0);
       umma::commit(bar);
     }
     mma_wait();
-    if (t == 0) load_piece(5);                                   // mlp.2
+    load_piece(5);                                   // mlp.2
     // ---- R10a: ReLU -> hidden operand chunks 0..11
     {
       auto r10a = [&](auto GGc) {
@@ -412,15 +440,16 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     umma::tc_fence_before();
     __syncthreads();
     // ---- R9b: mlp.0 output rows 96..175 (the first accumulator is consumed)
+    const uint32_t b5 = use_piece();
     if (t == 0) {
-      const uint32_t b = use_piece();
+      use_wait();
       umma::tc_fence_after();
-      issue_ts(D_ML0, C_XL, b, 80, 80, 11, 0);
+      issue_ts(D_ML0, C_XL, b5, 80, 80, 11, 0);
       umma::commit(bar);
     }
     x_issue(in_row);                                             // fp32 residual input of R12: two GEMMs ahead of its use
     mma_wait();
-    if (t == 0) load_piece(6);                                   // SRDF head layer 0 (hi | lo)
+    load_piece(6);                                   // SRDF head layer 0 (hi | lo)
     // ---- R10b: ReLU -> hidden operand chunks 12..21 (over the dead [LN1 | x] operand)
     {
       auto r10b = [&](auto GGc) {
@@ -440,14 +469,15 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     umma::tc_fence_before();
     __syncthreads();
     // ---- R11: mlp.2
+    const uint32_t b6 = use_piece();
     if (t == 0) {
-      const uint32_t b = use_piece();
+      use_wait();
       umma::tc_fence_after();
-      issue_ts(D_ML2, C_H1, b, 96, 96, 11, 0);
+      issue_ts(D_ML2, C_H1, b6, 96, 96, 11, 0);
       umma::commit(bar);
     }
     mma_wait();
-    if (t == 0 && has_next) load_piece(0);                       // the next tile's Wkv
+    if (has_next) load_piece(0);                       // the next tile's Wkv
     // ---- R12: LayerNorm 2, residual in fp32 from the fp32 input, split hi/lo for the SRDF head
     {
       auto r12 = [&](auto GGc) {
@@ -459,7 +489,7 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
         umma::tmem_ld_wait();
         red[GG * 128 + r] = ln_partial<NC>(v);
         umma::tc_fence_before();
-        __syncthreads();
+        pair_sync();
         const float2 st = ln2_stats(red, r, 1.f / 88.f);
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
@@ -492,18 +522,19 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     umma::tc_fence_before();
     __syncthreads();
     // ---- R13: DensityMLP layer 0 in split precision: r_hi.W_hi + r_lo.W_hi + r_hi.W_lo   (ray_transformer.py:147-150)
+    const uint32_t b7 = use_piece();
     if (t == 0) {
-      const uint32_t b = use_piece();
+      use_wait();
       umma::tc_fence_after();
-      issue_ts(D_DEN, C_RHI, b, 32, 32, 6, 0);
-      issue_ts(D_DEN, C_RLO, b, 32, 32, 6, 1);
-      issue_ts(D_DEN, C_RHI, b + 32 * 96 * 2, 32, 32, 6, 1);
+      issue_ts(D_DEN, C_RHI, b7, 32, 32, 6, 0);
+      issue_ts(D_DEN, C_RLO, b7, 32, 32, 6, 1);
+      issue_ts(D_DEN, C_RHI, b7 + 32 * 96 * 2, 32, 32, 6, 1);
       umma::commit(bar);
     }
     if (has_next) x_issue(in_row_nx);                            // the next tile's x: under the SRDF-head GEMM and its tail
     in_row_cur = in_row_nx;
     mma_wait();
-    if (t == 0 && has_next) load_piece(1);                       // the next tile's Wq
+    if (has_next) load_piece(1);                       // the next tile's Wq
     // ---- R14: DensityMLP tail 32 -> 16 -> 1 in fp32 (hidden units 8 g .. 8 g + 7 per thread)
     {
       float h[32];
@@ -528,7 +559,7 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
       };
       UFO_G2_DISPATCH(tail)
       umma::tc_fence_before();
-      __syncthreads();
+      pair_sync();
       if (g == 0 && row_ok) srdf[prow] = prm.db4 + (part_s[r] + part_s[128 + r]);
     }
     // the scratch is rewritten by the next tile's R2a only after its R0 barrier; TMEM is rewritten after that barrier too

@@ -113,7 +113,16 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
   constexpr uint32_t D_QKV = 0, D_RAD = 240, D_MRG = 144, D_ML0 = 80, D_ML2 = 80;
   extern __shared__ __align__(1024) uint8_t tc_smem[];
   uint8_t* const smem = tc_smem;
+  // The warp index goes through a shuffle so that the compiler can prove it warp-uniform: the half (hf), the TMEM base and the
+  // token-tile address then live in uniform registers, and the elected thread's tcgen05.mma operands (descriptors, TMEM addresses)
+  // are built on the uniform datapath.  With hf = tid >> 8 as plain thread arithmetic every MMA was wrapped in an
+  // ELECT / R2UR.BROADCAST / BRA.U.ANY loop: 19 dependent instructions per MMA in the issuing thread (-DUFO_NO_UNIFORM_ISSUE: old form).
+#ifndef UFO_NO_UNIFORM_ISSUE
+  const int tid = threadIdx.x, lane = tid & 31, warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int hf = warp_u >> 3, t = tid & 255, wl = warp_u & 7;
+#else
   const int tid = threadIdx.x, hf = tid >> 8, t = tid & 255, lane = tid & 31, wl = t >> 5;
+#endif
   const int q = wl & 3, g = wl >> 2, r = q * 32 + lane;
   const int gr = r % GR;                                // row inside its exchange group
   const int pl = (r / GR) * PPW + gr / L, l = gr % L;
@@ -149,7 +158,11 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
   umma::tc_fence_before();
   __syncthreads();
   umma::tc_fence_after();
+#ifndef UFO_NO_UNIFORM_ISSUE
+  const uint32_t tm = __shfl_sync(0xffffffffu, *tmem_slot, 0) + 256u * hf;
+#else
   const uint32_t tm = *tmem_slot + 256u * hf;
+#endif
   const uint32_t tl = tm + ((uint32_t)(q * 32) << 16);
   const uint32_t sm_base = umma::smem_u32(smem);
   const uint32_t x_base = umma::smem_u32(hs + V2H_X);
@@ -197,6 +210,41 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
     else umma::bar_sync(xbar_id, 64);
   };
 
+  // masked softmax over the views and colour blend of one tile (ray_transformer.py:316-320): one thread per point, warp 0 of the half.
+  // It runs DEFERRED, under the next tile's QKV GEMM (or after the loop for the last tile): at the end of its own tile it was serial work
+  // of one warp that the other seven waited for at the next barrier (-DUFO_VIEW_BLEND_INLINE: the old place).
+  auto blend = [&](int pb) {
+    if (t < PPT && pb + t < P) {
+      const size_t p = (size_t)slot_of(pb + t);
+      const int rr0 = (t / PPW) * GR + (t % PPW) * L + 1;        // row of (point t, view 0)
+      float om[NV];
+      float4 col[NV];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int n = 0; n < NV; ++n) {
+        col[n] = s_rgbm[t * NV + n];
+        const float w = prm.rb4 + (omg[rr0 + n] + omg[128 + rr0 + n]);
+        om[n] = (col[n].w == 0.f) ? -1e9f : w;                     // ray_transformer.py:316
+        mx = fmaxf(mx, om[n]);
+      }
+      float den = 0.f;
+#pragma unroll
+      for (int n = 0; n < NV; ++n) {
+        om[n] = ex2_ftz((om[n] - mx) * 1.4426950408889634f);
+        den += om[n];
+      }
+      float cr = 0.f, cg = 0.f, cb = 0.f;
+#pragma unroll
+      for (int n = 0; n < NV; ++n) {
+        const float pw = om[n] / den;
+        cr = fmaf(col[n].x, pw, cr);
+        cg = fmaf(col[n].y, pw, cg);
+        cb = fmaf(col[n].z, pw, cb);
+      }
+      radiance[p] = make_float4(cr, cg, cb, 0.f);
+    }
+  };
+  int prev_pbase = -1;
   for (; tile < n_tiles; tile += tstep) {
     const int pbase = tile * PPT;
     const int my_p = pbase + pl;
@@ -228,6 +276,9 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
       const int pp = pbase + t / NV;
       if (pp < P) my_col = __ldg(rgbm + (size_t)slot_of(pp) * NV + (t % NV));
     }
+#ifndef UFO_VIEW_BLEND_INLINE
+    if (prev_pbase >= 0) blend(prev_pbase);                      // the previous tile's colours, under this tile's QKV GEMM
+#endif
     half_wait();
     // ---- P2+P3: elu+1 on q, k; msg_l = sum_s (Q_l.K_s) V_s / (sum_s Q_l.K_s + 1e-6) per head over the L token rows of
     //      the point (== Q (K^T V) Z, linear_attention.py:36-45), K'/V' of the other rows by warp shuffle.
@@ -464,41 +515,23 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
       };
       UFO_G2_DISPATCH(tail)
     }
+#ifdef UFO_VIEW_BLEND_INLINE
     umma::tc_fence_before();
     umma::bar_sync(bar_id, 256);
-    if (t < PPT && pbase + t < P) {
-      const size_t p = (size_t)slot_of(pbase + t);
-      const int rr0 = (t / PPW) * GR + (t % PPW) * L + 1;        // row of (point t, view 0)
-      float om[NV];
-      float4 col[NV];
-      float mx = -INFINITY;
-#pragma unroll
-      for (int n = 0; n < NV; ++n) {
-        col[n] = s_rgbm[t * NV + n];
-        const float w = prm.rb4 + (omg[rr0 + n] + omg[128 + rr0 + n]);
-        om[n] = (col[n].w == 0.f) ? -1e9f : w;                     // ray_transformer.py:316
-        mx = fmaxf(mx, om[n]);
-      }
-      float den = 0.f;
-#pragma unroll
-      for (int n = 0; n < NV; ++n) {
-        om[n] = ex2_ftz((om[n] - mx) * 1.4426950408889634f);
-        den += om[n];
-      }
-      float cr = 0.f, cg = 0.f, cb = 0.f;
-#pragma unroll
-      for (int n = 0; n < NV; ++n) {
-        const float pw = om[n] / den;
-        cr = fmaf(col[n].x, pw, cr);
-        cg = fmaf(col[n].y, pw, cg);
-        cb = fmaf(col[n].z, pw, cb);
-      }
-      radiance[p] = make_float4(cr, cg, cb, 0.f);
-    }
+    blend(pbase);
+#else
+    prev_pbase = pbase;         // blended after the next P0 barrier, which also publishes omg
+#endif
     // omg / s_rgbm are next written after several more barriers of this half; the next tile's QKV MMA overwrites TMEM only
     // after its P0 barrier, which every thread reaches after its last TMEM read above
   }
   cp_async_wait_all();
+#ifndef UFO_VIEW_BLEND_INLINE
+  if (prev_pbase >= 0) {                                         // the last tile of this half
+    umma::bar_sync(bar_id, 256);
+    blend(prev_pbase);
+  }
+#endif
   umma::tc_fence_before();
   __syncthreads();
   if (tid < 32) umma::tmem_dealloc(*tmem_slot, 512);
