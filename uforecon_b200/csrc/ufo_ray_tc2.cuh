@@ -92,6 +92,14 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
   // warp index through a shuffle: provably warp-uniform, so that TMEM addresses and the column-group dispatch run on the uniform datapath
   const int t = threadIdx.x, lane = t & 31, wl = __shfl_sync(0xffffffffu, t >> 5, 0);
   const int q = wl & 3, g = wl >> 2, r = q * 32 + lane;
+  // the thread that issues the MMAs / the weight copies: one elected lane of warp 0 / warp 4 (-DUFO_NO_ELECT_ISSUE: threads 0 / 128)
+#ifndef UFO_NO_ELECT_ISSUE
+#define UFO_RAY_ISSUER (wl == 0 && umma::elect_one())
+#define UFO_RAY_LOADER (wl == kLoadThread / 32 && umma::elect_one())
+#else
+#define UFO_RAY_ISSUER (t == 0)
+#define UFO_RAY_LOADER (t == kLoadThread)
+#endif
   const long long n_tiles = (P + 127) / 128;
 
   if (wl == 0) umma::tmem_alloc(tmem_slot, 256);
@@ -133,7 +141,7 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     ++pc_load;
     // the copies are issued by a thread of warp 4: the g = 1 warps own 5 of the 11 chunks of a row, so they reach the end of an
     // epilogue first, and warp 0 (which issues the MMAs) starts its epilogue without this detour (-DUFO_RAY_LOAD_T0: thread 0)
-    if (t == kLoadThread) bulk_load(smem + R2_SLOT + s * R2_SLOT_BYTES, wimg + off[j], len[j], full + s);
+    if (UFO_RAY_LOADER) bulk_load(smem + R2_SLOT + s * R2_SLOT_BYTES, wimg + off[j], len[j], full + s);
   };
   // every thread: slot and parity of the piece about to be used; thread 0 waits until it has landed (use_wait) before it issues
   uint32_t use_s = 0, use_par = 0;
@@ -145,6 +153,19 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     return sm_base + R2_SLOT + use_s * R2_SLOT_BYTES;
   };
   auto use_wait = [&]() { umma::mbar_wait(full + use_s, use_par); };
+  // -DUFO_RAY_PREWAIT: the issuer waits for the piece of the NEXT GEMM right after the commit of the current one (while its MMAs run)
+  // instead of in front of the next issue.  Measured on a B200: no gain (ray stage 167.9 vs 166.3 ms per map without it) - the wait on a
+  // completed phase is cheap next to the phase itself, and the extra wait delays the issuing warp's own epilogue.  Not the default.
+  auto commit_and_prewait = [&](bool next_exists) {
+    umma::commit(bar);
+#ifdef UFO_RAY_PREWAIT
+    if (next_exists) {
+      const uint32_t ns = pc_use & 1;
+      umma::mbar_wait(full + ns, (fph >> ns) & 1u);
+    }
+#endif
+  };
+  bool first_gemm = true;
   // the two warps that share the token rows 32 q .. 32 q + 31 (column halves g = 0, 1): a 64-thread named barrier where only they
   // exchange data (LayerNorm / SRDF partials); -DUFO_RAY_CTA_SYNC restores the CTA-wide barrier
   auto pair_sync = [&]() {
@@ -163,8 +184,9 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
   auto issue_ts = [&](uint32_t d_col, uint32_t a_col, uint32_t b_addr, uint32_t b_rows, uint32_t n, int ksteps, uint32_t acc_first) {
     const uint32_t idesc = umma::make_idesc(128, n, FMT, false, false);
     const uint32_t lbo = b_rows * 16u;
+    const uint32_t lo0 = umma::desc_lo(b_addr, lbo);             // one K step = two chunks = 2 * lbo bytes = 2 * b_rows descriptor units
     for (int ks = 0; ks < ksteps; ++ks)
-      umma::mma_f16_ts(tm + d_col, tm + a_col + 8 * ks, umma::make_smem_desc(b_addr + 2 * ks * lbo, lbo, 128u), idesc, ks > 0 ? 1u : acc_first);
+      umma::mma_f16_ts_lh(tm + d_col, tm + a_col + 8 * ks, lo0 + (uint32_t)ks * 2u * b_rows, umma::desc_hi(128u), idesc, ks > 0 ? 1u : acc_first);
   };
 
   if ((long long)blockIdx.x < n_tiles) {
@@ -229,12 +251,17 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     __syncthreads();
     // ---- R1a: k | v = x . Wkv^T
     const uint32_t b1 = use_piece();
-    if (t == 0) {
+    if (UFO_RAY_ISSUER) {
+#ifdef UFO_RAY_PREWAIT
+      if (first_gemm) use_wait();
+#else
       use_wait();
+#endif
       umma::tc_fence_after();
       issue_ts(D_KV, C_X, b1, 176, 176, 6, 0);
-      umma::commit(bar);
+      commit_and_prewait(true);
     }
+    first_gemm = false;
     mma_wait();
     load_piece(2);                                   // merge weights -> the slot Wkv leaves
     // ---- R2a: K' = elu(k)+1, V' = v -> MN-major operand tiles in shared memory   (linear_attention.py:36-41)
@@ -264,11 +291,13 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     __syncthreads();
     // ---- R1b: q = x . Wq^T   (the k | v accumulator is consumed)
     const uint32_t b2 = use_piece();
-    if (t == 0) {
+    if (UFO_RAY_ISSUER) {
+#ifndef UFO_RAY_PREWAIT
       use_wait();
+#endif
       umma::tc_fence_after();
       issue_ts(D_Q, C_X, b2, 96, 96, 6, 0);
-      umma::commit(bar);
+      commit_and_prewait(true);
     }
     mma_wait();
     load_piece(3);                                   // mlp.0 rows 0..95
@@ -295,16 +324,16 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     umma::tc_fence_before();
     __syncthreads();
     // ---- R3: per sequence  D[b][a] = sum_s V'[s][b] K'[s][a]   (rows 88..95 = sum_s K'[s][a]);  both operands MN-major
-    if (t == 0) {
+    if (UFO_RAY_ISSUER) {
       umma::tc_fence_after();
       const uint32_t idesc = umma::make_idesc(128, 96, FMT, true, true);
+      const uint32_t alo = umma::desc_lo(sm_base + R2_V, 128), blo = umma::desc_lo(sm_base + R2_K, 128);
 #pragma unroll
       for (int sq = 0; sq < NSEQ; ++sq) {
+#pragma unroll
         for (int ks = 0; ks < SN / 16; ++ks) {
-          const uint32_t off = (uint32_t)(sq * (SN / 16) + ks) * 256u;
-          const uint64_t ad = umma::make_smem_desc(sm_base + R2_V + off, 128, kChunk);
-          const uint64_t bd = umma::make_smem_desc(sm_base + R2_K + off, 128, kChunk);
-          umma::mma_f16(tm + (sq == 0 ? D_S0 : D_S1), ad, bd, idesc, ks > 0);
+          const uint32_t off = (uint32_t)(sq * (SN / 16) + ks) * (256u >> 4);      // 16 token rows = 256 bytes of an MN-major tile
+          umma::mma_f16_lh(tm + (sq == 0 ? D_S0 : D_S1), alo + off, umma::desc_hi(kChunk), blo + off, umma::desc_hi(kChunk), idesc, ks > 0);
         }
       }
       umma::commit(bar);
@@ -337,7 +366,7 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     umma::tc_fence_before();
     __syncthreads();
     // ---- R5: message numerator Q'.KV_h (columns 0..87) and per-head normalisers Q'_h.Ksum_h (columns 88..95)
-    if (t == 0) {
+    if (UFO_RAY_ISSUER) {
       umma::tc_fence_after();
 #pragma unroll
       for (int sq = 0; sq < NSEQ; ++sq) issue_ts(sq == 0 ? D_S0 : D_S1, C_QP, sm_base + (sq == 0 ? R2_K : R2_V), 96, 96, 6, 0);
@@ -375,11 +404,13 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     __syncthreads();
     // ---- R7: merge
     const uint32_t b3 = use_piece();
-    if (t == 0) {
+    if (UFO_RAY_ISSUER) {
+#ifndef UFO_RAY_PREWAIT
       use_wait();
+#endif
       umma::tc_fence_after();
       issue_ts(D_MRG, C_M, b3, 96, 96, 6, 0);
-      umma::commit(bar);
+      commit_and_prewait(true);
     }
     if (NSEQ > 1) x_issue(in_row);                               // x again, for the [LN1 | x] operand: under the merge GEMM
     mma_wait();
@@ -413,11 +444,13 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     __syncthreads();
     // ---- R9a: mlp.0 on [LN1 | x]  (K = 176), output rows 0..95
     const uint32_t b4 = use_piece();
-    if (t == 0) {
+    if (UFO_RAY_ISSUER) {
+#ifndef UFO_RAY_PREWAIT
       use_wait();
+#endif
       umma::tc_fence_after();
       issue_ts(D_ML0, C_XL, b4, 96, 96, 11, 0);
-      umma::commit(bar);
+      commit_and_prewait(true);
     }
     mma_wait();
     load_piece(5);                                   // mlp.2
@@ -441,11 +474,13 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     __syncthreads();
     // ---- R9b: mlp.0 output rows 96..175 (the first accumulator is consumed)
     const uint32_t b5 = use_piece();
-    if (t == 0) {
+    if (UFO_RAY_ISSUER) {
+#ifndef UFO_RAY_PREWAIT
       use_wait();
+#endif
       umma::tc_fence_after();
       issue_ts(D_ML0, C_XL, b5, 80, 80, 11, 0);
-      umma::commit(bar);
+      commit_and_prewait(true);
     }
     x_issue(in_row);                                             // fp32 residual input of R12: two GEMMs ahead of its use
     mma_wait();
@@ -470,11 +505,13 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     __syncthreads();
     // ---- R11: mlp.2
     const uint32_t b6 = use_piece();
-    if (t == 0) {
+    if (UFO_RAY_ISSUER) {
+#ifndef UFO_RAY_PREWAIT
       use_wait();
+#endif
       umma::tc_fence_after();
       issue_ts(D_ML2, C_H1, b6, 96, 96, 11, 0);
-      umma::commit(bar);
+      commit_and_prewait(true);
     }
     mma_wait();
     if (has_next) load_piece(0);                       // the next tile's Wkv
@@ -523,13 +560,15 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     __syncthreads();
     // ---- R13: DensityMLP layer 0 in split precision: r_hi.W_hi + r_lo.W_hi + r_hi.W_lo   (ray_transformer.py:147-150)
     const uint32_t b7 = use_piece();
-    if (t == 0) {
+    if (UFO_RAY_ISSUER) {
+#ifndef UFO_RAY_PREWAIT
       use_wait();
+#endif
       umma::tc_fence_after();
       issue_ts(D_DEN, C_RHI, b7, 32, 32, 6, 0);
       issue_ts(D_DEN, C_RLO, b7, 32, 32, 6, 1);
       issue_ts(D_DEN, C_RHI, b7 + 32 * 96 * 2, 32, 32, 6, 1);
-      umma::commit(bar);
+      commit_and_prewait(has_next);
     }
     if (has_next) x_issue(in_row_nx);                            // the next tile's x: under the SRDF-head GEMM and its tail
     in_row_cur = in_row_nx;
@@ -567,6 +606,8 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
   umma::tc_fence_before();
   __syncthreads();
   if (wl == 0) umma::tmem_dealloc(tm, 256);
+#undef UFO_RAY_ISSUER
+#undef UFO_RAY_LOADER
 }
 
 }  // namespace ufo

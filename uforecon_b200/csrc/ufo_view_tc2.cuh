@@ -64,6 +64,25 @@ __host__ __device__ constexpr int view2_group_rows(int nv) {
 }
 __host__ __device__ constexpr int view2_points_per_tile(int nv) { return (128 / view2_group_rows(nv)) * (view2_group_rows(nv) / (nv + 1)); }
 
+// K loop of an SS-form GEMM (A: 128-row K-major tile at a_base, B: K-major weight tile with b_rows rows at b_base) with the descriptors
+// advanced by one 32-bit add per K step (ufo_umma.cuh: desc_lo / desc_hi)
+__device__ __forceinline__ void issue_gemm_lh(uint32_t tmem_d, uint32_t a_base, uint32_t b_base, uint32_t b_rows, uint32_t k_chunks,
+                                              uint32_t idesc, uint32_t acc_first) {
+  const uint32_t a0 = umma::desc_lo(a_base, kChunk), b0 = umma::desc_lo(b_base, b_rows * 16u);
+#pragma unroll
+  for (uint32_t c = 0; c < k_chunks; c += 2)
+    umma::mma_f16_lh(tmem_d, a0 + c * (kChunk >> 4), umma::desc_hi(128u), b0 + c * b_rows, umma::desc_hi(128u), idesc, (c > 0) ? 1u : acc_first);
+}
+// K loop of a TS-form GEMM: A chunk pairs from the TMEM columns a_col(ks), B K-major weight tile (b_rows rows) from K step k0 on
+template <typename ACol>
+__device__ __forceinline__ void issue_ts_lh(uint32_t tmem_d, ACol a_col, uint32_t b_base, uint32_t b_rows, int k0, int ksteps, uint32_t idesc,
+                                            uint32_t acc_first) {
+  const uint32_t b0 = umma::desc_lo(b_base, b_rows * 16u);
+#pragma unroll
+  for (int ks = 0; ks < ksteps; ++ks)
+    umma::mma_f16_ts_lh(tmem_d, a_col(ks), b0 + (uint32_t)(k0 + ks) * 2u * b_rows, umma::desc_hi(128u), idesc, ks > 0 ? 1u : acc_first);
+}
+
 #define UFO_G2_DISPATCH(fn)     \
   if (g == 0) fn(IC<0>{});      \
   else fn(IC<1>{});
@@ -124,6 +143,12 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
   const int tid = threadIdx.x, hf = tid >> 8, t = tid & 255, lane = tid & 31, wl = t >> 5;
 #endif
   const int q = wl & 3, g = wl >> 2, r = q * 32 + lane;
+  // the thread of a half that issues its MMAs: one elected lane of the half's warp 0 (-DUFO_NO_ELECT_ISSUE: thread 0 of the half)
+#if !defined(UFO_NO_ELECT_ISSUE) && !defined(UFO_NO_UNIFORM_ISSUE)
+#define UFO_VIEW_ISSUER (wl == 0 && umma::elect_one())
+#else
+#define UFO_VIEW_ISSUER (t == 0)
+#endif
   const int gr = r % GR;                                // row inside its exchange group
   const int pl = (r / GR) * PPW + gr / L, l = gr % L;
   const bool row_ok = gr < RPW;
@@ -257,11 +282,11 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
     umma::tc_fence_before();
     umma::bar_sync(bar_id, 256);
     // ---- P1: q|k|v = X . Wqkv^T (transformer.py:47) and the x part of the radiance head's first layer
-    if (t == 0) {
+    if (UFO_VIEW_ISSUER) {
       umma::tc_fence_after();
-      issue_gemm_sub(tm + D_QKV, xb, sm_base + V2_WQKV, 240, 0, 10, umma::make_idesc(128, 240, FMT, false, false), 0);
+      issue_gemm_lh(tm + D_QKV, xb, sm_base + V2_WQKV, 240, 10, umma::make_idesc(128, 240, FMT, false, false), 0);
       umma::commit(bar);
-      issue_gemm_sub(tm + D_RAD, xb, sm_base + V2_WRAD, 16, 0, 10, umma::make_idesc(128, 16, FMT, false, false), 0);
+      issue_gemm_lh(tm + D_RAD, xb, sm_base + V2_WRAD, 16, 10, umma::make_idesc(128, 16, FMT, false, false), 0);
     }
     float3 my_dir = make_float3(0.f, 0.f, 0.f);
     if (live && l > 0 && g == 0) {
@@ -350,14 +375,10 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
     umma::tc_fence_before();
     umma::bar_sync(bar_id, 256);
     // ---- P4: merge (transformer.py:55), A from TMEM
-    if (t == 0) {
+    if (UFO_VIEW_ISSUER) {
       umma::tc_fence_after();
-      const uint32_t idesc = umma::make_idesc(128, 80, FMT, false, false);
-      constexpr uint32_t lbo = 80 * 16;
-#pragma unroll
-      for (int ks = 0; ks < 6; ++ks)
-        umma::mma_f16_ts(tm + D_MRG, tm + 120 * (ks / 3) + 8 * (ks % 3), umma::make_smem_desc(sm_base + V2_WMRG + 2 * ks * lbo, lbo, 128u),
-                         idesc, ks > 0);
+      issue_ts_lh(tm + D_MRG, [&](int ks) { return tm + 120 * (ks / 3) + 8 * (ks % 3); }, sm_base + V2_WMRG, 80, 0, 6,
+                  umma::make_idesc(128, 80, FMT, false, false), 0);
       umma::commit(bar);
     }
     if (t < PPT * NV) s_rgbm[t] = my_col;
@@ -370,9 +391,9 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
         red[GG * 128 + r] = ln40_load(tl + D_MRG + 40 * GG, v);
         umma::tc_fence_before();
         umma::bar_sync(bar_id, 256);
-        if (GG == 0 && t == 0) {   // the merge accumulator is consumed: the x half of mlp.0 runs under the rest of this phase
+        if (GG == 0 && UFO_VIEW_ISSUER) {   // the merge accumulator is consumed: the x half of mlp.0 runs under the rest of this phase
           umma::tc_fence_after();
-          issue_gemm_sub(tm + D_ML0, xb, sm_base + V2_WML0, 160, 0, 10, umma::make_idesc(128, 160, FMT, false, false), 0);
+          issue_gemm_lh(tm + D_ML0, xb, sm_base + V2_WML0, 160, 10, umma::make_idesc(128, 160, FMT, false, false), 0);
         }
         const float2 st = ln2_stats(red, r, 1.f / 80.f);
         uint32_t o[24];
@@ -394,14 +415,10 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
     umma::tc_fence_before();
     umma::bar_sync(bar_id, 256);
     // ---- P6: mlp.0 on [x | LN1]  (transformer.py:57): message half from TMEM on top of the x half issued inside P5
-    if (t == 0) {
+    if (UFO_VIEW_ISSUER) {
       umma::tc_fence_after();
-      const uint32_t idesc = umma::make_idesc(128, 160, FMT, false, false);
-      constexpr uint32_t lbo = 160 * 16;
-#pragma unroll
-      for (int ks = 0; ks < 6; ++ks)
-        umma::mma_f16_ts(tm + D_ML0, tm + 24 * (ks / 3) + 8 * (ks % 3),
-                         umma::make_smem_desc(sm_base + V2_WML0 + (10 + 2 * ks) * lbo, lbo, 128u), idesc, 1u);
+      issue_ts_lh(tm + D_ML0, [&](int ks) { return tm + 24 * (ks / 3) + 8 * (ks % 3); }, sm_base + V2_WML0, 160, 5, 6,
+                  umma::make_idesc(128, 160, FMT, false, false), 1u);
       umma::commit(bar);
     }
     half_wait();
@@ -428,13 +445,9 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
     umma::tc_fence_before();
     umma::bar_sync(bar_id, 256);
     // ---- P8: mlp.2
-    if (t == 0) {
+    if (UFO_VIEW_ISSUER) {
       umma::tc_fence_after();
-      const uint32_t idesc = umma::make_idesc(128, 80, FMT, false, false);
-      constexpr uint32_t lbo = 80 * 16;
-#pragma unroll
-      for (int ks = 0; ks < 10; ++ks)
-        umma::mma_f16_ts(tm + D_ML2, tm + 8 * ks, umma::make_smem_desc(sm_base + V2_WML2 + 2 * ks * lbo, lbo, 128u), idesc, ks > 0);
+      issue_ts_lh(tm + D_ML2, [&](int ks) { return tm + 8 * ks; }, sm_base + V2_WML2, 80, 0, 10, umma::make_idesc(128, 80, FMT, false, false), 0);
       umma::commit(bar);
     }
     half_wait();
@@ -479,14 +492,10 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
     umma::tc_fence_before();
     umma::bar_sync(bar_id, 256);
     // ---- P10: LN2 / direction / bias part of the radiance head's first layer   (ray_transformer.py:159-163,313)
-    if (t == 0) {
+    if (UFO_VIEW_ISSUER) {
       umma::tc_fence_after();
-      const uint32_t idesc = umma::make_idesc(128, 16, FMT, false, false);
-      constexpr uint32_t lbo = 16 * 16;
-#pragma unroll
-      for (int ks = 0; ks < 6; ++ks)
-        umma::mma_f16_ts(tm + D_RAD, tm + 24 * (ks / 3) + 8 * (ks % 3),
-                         umma::make_smem_desc(sm_base + V2_WRAD + (10 + 2 * ks) * lbo, lbo, 128u), idesc, 1u);
+      issue_ts_lh(tm + D_RAD, [&](int ks) { return tm + 24 * (ks / 3) + 8 * (ks % 3); }, sm_base + V2_WRAD, 16, 5, 6,
+                  umma::make_idesc(128, 16, FMT, false, false), 1u);
       umma::commit(bar);
     }
     half_wait();
@@ -535,6 +544,7 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
   umma::tc_fence_before();
   __syncthreads();
   if (tid < 32) umma::tmem_dealloc(*tmem_slot, 512);
+#undef UFO_VIEW_ISSUER
 }
 
 }  // namespace ufo
