@@ -95,9 +95,13 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
   // the thread that issues the MMAs / the weight copies: one elected lane of warp 0 / warp 4 (-DUFO_NO_ELECT_ISSUE: threads 0 / 128)
 #ifndef UFO_NO_ELECT_ISSUE
 #define UFO_RAY_ISSUER (wl == 0 && umma::elect_one())
+#define UFO_RAY_ISSUE_WARP (wl == 0)          // GEMMs that wait for a weight piece: the whole warp waits, then one lane is elected
+#define UFO_RAY_ELECT (umma::elect_one())
 #define UFO_RAY_LOADER (wl == kLoadThread / 32 && umma::elect_one())
 #else
 #define UFO_RAY_ISSUER (t == 0)
+#define UFO_RAY_ISSUE_WARP (t == 0)
+#define UFO_RAY_ELECT (true)
 #define UFO_RAY_LOADER (t == kLoadThread)
 #endif
   const long long n_tiles = (P + 127) / 128;
@@ -193,37 +197,65 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     load_piece(0);
     load_piece(1);
   }
-  // Input row of this thread's token in a tile.  With sorted samples it goes through the sort permutation: that byte load is issued
-  // by inline asm at the program position of the call (one tile ahead, see below) - as plain C++ the compiler sank it next to its
-  // first use, and 10 % of the kernel's stall samples waited on the perm -> address -> x dependency chain.
-  auto in_row_of = [&](long long tile) -> long long {
-    const long long prow = tile * 128 + r;
-    if (prow >= P) return -1;
-    if (SN == kNC) return tc_slot(prow, 0);
-    if (perm == nullptr) return tile * 128 + r;
-    unsigned pv;
-    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(pv) : "l"(perm + prow));
-    return tile * 128 + (long long)pv;
-  };
-  // chunk c (8 channels) of this row's fp32 input: view-stage output (c < 10) or order encoding (c == 10)
-  auto x_chunk = [&](long long ir, int c, float4& a, float4& b) {
-    a = b = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c < 10) {
-      if (ir >= 0) {
-        a = __ldg(reinterpret_cast<const float4*>(vout0 + (size_t)ir * kDView + 8 * c));
-        b = __ldg(reinterpret_cast<const float4*>(vout0 + (size_t)ir * kDView + 8 * c + 4));
-      }
-    } else if (c == 10) {
-      a = __ldg(reinterpret_cast<const float4*>(pe_table + (r % SN) * 8));       // ray_transformer.py:301-303
-      b = __ldg(reinterpret_cast<const float4*>(pe_table + (r % SN) * 8 + 4));
+  // Input row of this thread's token in a tile.  With sorted samples it goes through the sort permutation.  The byte load is issued by
+  // inline asm ONE TILE AHEAD (perm_load, at the top of the previous tile) and its first use is pinned to the place where the row is
+  // needed (in_row_from, in front of the x loads of R13) by an empty asm: as plain C++ the compiler sank the load next to its first use
+  // (10 % of the stall samples on the perm -> address -> x chain), and with only the load pinned it put the address add right behind
+  // the load (3 % of the samples at the top of every tile).  Rows past P read the last valid byte (branch-free) and are dropped later.
+  auto perm_load = [&](long long tile) -> unsigned {
+    unsigned pv = 0;
+    if (SN != kNC && perm != nullptr) {                      // uniform
+      const long long prow = tile * 128 + r;
+      asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(pv) : "l"(perm + (prow < P ? prow : P - 1)));
     }
+    return pv;
   };
-  // This thread's half of the fp32 input row, chunks 6 g .. 6 g + 5 (g = 1: chunk 10 is the order encoding, chunk 11 zero):
-  // the loads are ISSUED ahead of an MMA wait and consumed after it, so that their L2 latency is not exposed
+  auto in_row_from = [&](long long tile, unsigned pv) -> long long {
+    const long long prow = tile * 128 + r;
+    if (SN == kNC) return prow < P ? tc_slot(prow, 0) : -1;
+    if (perm == nullptr) return prow < P ? prow : -1;
+    asm volatile("" : "+r"(pv));
+    return prow < P ? tile * 128 + (long long)pv : -1;
+  };
+  // 16 bytes of read-only global memory, or zeros: ONE predicated load, no branch.  (As `if (ok) v = __ldg(p)` under the row / chunk
+  // conditions the twelve loads of a row sat in four conditional blocks, and the warp waited for the loads already in flight at every
+  // one of those branches: 15 % of the kernel's stall samples were in x_issue, more than in the MMA waits it is meant to hide under.)
+  auto ldg4_pred = [](const float* ptr, bool ok) -> float4 {
+    float4 v;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.f32 %0, 0f00000000;\n\t"
+        "mov.f32 %1, 0f00000000;\n\t"
+        "mov.f32 %2, 0f00000000;\n\t"
+        "mov.f32 %3, 0f00000000;\n\t"
+        "@p ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t"
+        "}"
+        : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+        : "l"(ptr), "r"((int)ok));
+    return v;
+  };
+  // This thread's half of the fp32 input row, chunks 6 g .. 6 g + 5: view-stage output (chunks 0..9), order encoding (chunk 10,
+  // ray_transformer.py:301-303), zero (chunk 11).  The loads are ISSUED ahead of an MMA wait and consumed after it, so that their L2
+  // latency is not exposed; straight-line code, the column half g only selects addresses and predicates.
   float4 xr[12];
   auto x_issue = [&](long long ir) {
+    const bool ok = ir >= 0;
+    const float* src = vout0 + (size_t)(ok ? ir : 0) * kDView + 48 * g;      // chunk 6 g of the row
+    const float* pe = pe_table + (r % SN) * 8;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) x_chunk(ir, 6 * g + i, xr[2 * i], xr[2 * i + 1]);
+    for (int i = 0; i < 4; ++i) {                                            // chunks 0..3 | 6..9
+      xr[2 * i] = ldg4_pred(src + 8 * i, ok);
+      xr[2 * i + 1] = ldg4_pred(src + 8 * i + 4, ok);
+    }
+    const float* p4 = g ? pe : src + 32;                                     // chunk 4 | 10 (order encoding)
+    const bool ok4 = g ? true : ok;
+    xr[8] = ldg4_pred(p4, ok4);
+    xr[9] = ldg4_pred(p4 + 4, ok4);
+    const bool ok5 = ok && g == 0;                                           // chunk 5 | 11 (zero)
+    xr[10] = ldg4_pred(src + 40, ok5);
+    xr[11] = ldg4_pred(src + 44, ok5);
   };
   // the loaded chunks as 16-bit operand chunks -> TMEM columns col0 + 4 c   (n_chunks: 12 for the QKV operand, 11 for [LN1 | x])
   auto x_store = [&](uint32_t col0, int n_chunks) {
@@ -235,7 +267,7 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
                        umma::pack2<BF16>(xr[2 * i + 1].x, xr[2 * i + 1].y), umma::pack2<BF16>(xr[2 * i + 1].z, xr[2 * i + 1].w));
     }
   };
-  long long in_row_cur = (long long)blockIdx.x < n_tiles ? in_row_of(blockIdx.x) : -1;
+  long long in_row_cur = (long long)blockIdx.x < n_tiles ? in_row_from(blockIdx.x, perm_load(blockIdx.x)) : -1;
   if ((long long)blockIdx.x < n_tiles) x_issue(in_row_cur);
 
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -243,7 +275,7 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     const bool row_ok = prow < P;
     const long long in_row = in_row_cur;             // looked up one tile ahead (in_row_nx of the previous iteration)
     const bool has_next = tile + (long long)gridDim.x < n_tiles;
-    const long long in_row_nx = has_next ? in_row_of(tile + gridDim.x) : -1;      // its perm lookup completes long before it is used
+    const unsigned pv_nx = has_next ? perm_load(tile + gridDim.x) : 0u;         // the next tile's perm byte: used in R13
     // ---- R0: x = [view-stage token 0 output | order encoding | 0] -> 16-bit A operand in TMEM (chunks 6 g .. 6 g + 5)
     x_store(C_X, 12);                                            // loads issued by the previous tile (or the prologue)
     umma::tmem_st_wait();
@@ -251,15 +283,17 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     __syncthreads();
     // ---- R1a: k | v = x . Wkv^T
     const uint32_t b1 = use_piece();
-    if (UFO_RAY_ISSUER) {
+    if (UFO_RAY_ISSUE_WARP) {
 #ifdef UFO_RAY_PREWAIT
       if (first_gemm) use_wait();
 #else
       use_wait();
 #endif
-      umma::tc_fence_after();
-      issue_ts(D_KV, C_X, b1, 176, 176, 6, 0);
-      commit_and_prewait(true);
+      if (UFO_RAY_ELECT) {
+        umma::tc_fence_after();
+        issue_ts(D_KV, C_X, b1, 176, 176, 6, 0);
+        commit_and_prewait(true);
+      }
     }
     first_gemm = false;
     mma_wait();
@@ -291,13 +325,15 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     __syncthreads();
     // ---- R1b: q = x . Wq^T   (the k | v accumulator is consumed)
     const uint32_t b2 = use_piece();
-    if (UFO_RAY_ISSUER) {
+    if (UFO_RAY_ISSUE_WARP) {
 #ifndef UFO_RAY_PREWAIT
       use_wait();
 #endif
-      umma::tc_fence_after();
-      issue_ts(D_Q, C_X, b2, 96, 96, 6, 0);
-      commit_and_prewait(true);
+      if (UFO_RAY_ELECT) {
+        umma::tc_fence_after();
+        issue_ts(D_Q, C_X, b2, 96, 96, 6, 0);
+        commit_and_prewait(true);
+      }
     }
     mma_wait();
     load_piece(3);                                   // mlp.0 rows 0..95
@@ -404,13 +440,15 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     __syncthreads();
     // ---- R7: merge
     const uint32_t b3 = use_piece();
-    if (UFO_RAY_ISSUER) {
+    if (UFO_RAY_ISSUE_WARP) {
 #ifndef UFO_RAY_PREWAIT
       use_wait();
 #endif
-      umma::tc_fence_after();
-      issue_ts(D_MRG, C_M, b3, 96, 96, 6, 0);
-      commit_and_prewait(true);
+      if (UFO_RAY_ELECT) {
+        umma::tc_fence_after();
+        issue_ts(D_MRG, C_M, b3, 96, 96, 6, 0);
+        commit_and_prewait(true);
+      }
     }
     if (NSEQ > 1) x_issue(in_row);                               // x again, for the [LN1 | x] operand: under the merge GEMM
     mma_wait();
@@ -444,13 +482,15 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     __syncthreads();
     // ---- R9a: mlp.0 on [LN1 | x]  (K = 176), output rows 0..95
     const uint32_t b4 = use_piece();
-    if (UFO_RAY_ISSUER) {
+    if (UFO_RAY_ISSUE_WARP) {
 #ifndef UFO_RAY_PREWAIT
       use_wait();
 #endif
-      umma::tc_fence_after();
-      issue_ts(D_ML0, C_XL, b4, 96, 96, 11, 0);
-      commit_and_prewait(true);
+      if (UFO_RAY_ELECT) {
+        umma::tc_fence_after();
+        issue_ts(D_ML0, C_XL, b4, 96, 96, 11, 0);
+        commit_and_prewait(true);
+      }
     }
     mma_wait();
     load_piece(5);                                   // mlp.2
@@ -474,13 +514,15 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     __syncthreads();
     // ---- R9b: mlp.0 output rows 96..175 (the first accumulator is consumed)
     const uint32_t b5 = use_piece();
-    if (UFO_RAY_ISSUER) {
+    if (UFO_RAY_ISSUE_WARP) {
 #ifndef UFO_RAY_PREWAIT
       use_wait();
 #endif
-      umma::tc_fence_after();
-      issue_ts(D_ML0, C_XL, b5, 80, 80, 11, 0);
-      commit_and_prewait(true);
+      if (UFO_RAY_ELECT) {
+        umma::tc_fence_after();
+        issue_ts(D_ML0, C_XL, b5, 80, 80, 11, 0);
+        commit_and_prewait(true);
+      }
     }
     x_issue(in_row);                                             // fp32 residual input of R12: two GEMMs ahead of its use
     mma_wait();
@@ -505,13 +547,15 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     __syncthreads();
     // ---- R11: mlp.2
     const uint32_t b6 = use_piece();
-    if (UFO_RAY_ISSUER) {
+    if (UFO_RAY_ISSUE_WARP) {
 #ifndef UFO_RAY_PREWAIT
       use_wait();
 #endif
-      umma::tc_fence_after();
-      issue_ts(D_ML2, C_H1, b6, 96, 96, 11, 0);
-      commit_and_prewait(true);
+      if (UFO_RAY_ELECT) {
+        umma::tc_fence_after();
+        issue_ts(D_ML2, C_H1, b6, 96, 96, 11, 0);
+        commit_and_prewait(true);
+      }
     }
     mma_wait();
     if (has_next) load_piece(0);                       // the next tile's Wkv
@@ -560,16 +604,19 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     __syncthreads();
     // ---- R13: DensityMLP layer 0 in split precision: r_hi.W_hi + r_lo.W_hi + r_hi.W_lo   (ray_transformer.py:147-150)
     const uint32_t b7 = use_piece();
-    if (UFO_RAY_ISSUER) {
+    if (UFO_RAY_ISSUE_WARP) {
 #ifndef UFO_RAY_PREWAIT
       use_wait();
 #endif
-      umma::tc_fence_after();
-      issue_ts(D_DEN, C_RHI, b7, 32, 32, 6, 0);
-      issue_ts(D_DEN, C_RLO, b7, 32, 32, 6, 1);
-      issue_ts(D_DEN, C_RHI, b7 + 32 * 96 * 2, 32, 32, 6, 1);
-      commit_and_prewait(has_next);
+      if (UFO_RAY_ELECT) {
+        umma::tc_fence_after();
+        issue_ts(D_DEN, C_RHI, b7, 32, 32, 6, 0);
+        issue_ts(D_DEN, C_RLO, b7, 32, 32, 6, 1);
+        issue_ts(D_DEN, C_RHI, b7 + 32 * 96 * 2, 32, 32, 6, 1);
+        commit_and_prewait(has_next);
+      }
     }
+    const long long in_row_nx = has_next ? in_row_from(tile + gridDim.x, pv_nx) : -1;
     if (has_next) x_issue(in_row_nx);                            // the next tile's x: under the SRDF-head GEMM and its tail
     in_row_cur = in_row_nx;
     mma_wait();
@@ -607,6 +654,8 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
   __syncthreads();
   if (wl == 0) umma::tmem_dealloc(tm, 256);
 #undef UFO_RAY_ISSUER
+#undef UFO_RAY_ISSUE_WARP
+#undef UFO_RAY_ELECT
 #undef UFO_RAY_LOADER
 }
 

@@ -40,7 +40,17 @@ constexpr uint32_t V2_WML2 = V2_WML0 + 160 * 176 * 2;        // [80][160]
 constexpr uint32_t V2_WRAD = V2_WML2 + 80 * 160 * 2;         // [16][176]   K: x 80 | LN2 g0 40 | dir 3, 1, 0 x4 | LN2 g1 40 | 0 x8
 constexpr uint32_t V2_WEND = V2_WRAD + 16 * 176 * 2;         // 141,312
 constexpr uint32_t V2H_X = 0;                                // per half: token operand, 10 chunks
-constexpr uint32_t V2H_XCH = 10 * kChunk;                    // per warp [32 rows][K' 10 | V 10] fp32: attention exchange of one head
+// Chunk stride (= LBO of the descriptor) of the token tile.  -DUFO_VIEW_TOK_CONTIG pads it by one 16-byte piece and fills the tile with
+// consecutive lanes on consecutive 16-byte pieces of the tile's CONTIGUOUS token block in global memory (4-5 cache lines per cp.async
+// instead of 24, bank-conflict-free writes thanks to the padding).  ncu counts 24 L1 wavefronts per cp.async in the default mapping
+// (lanes on consecutive rows of one chunk, 160 bytes apart in global memory), 22 % of the kernel's shared-memory/L1 wavefronts - but
+// the copies run a whole tile ahead and nothing waits for them: measured 230.7 ms per map against 229.4 ms for the default, not kept.
+#ifdef UFO_VIEW_TOK_CONTIG
+constexpr uint32_t V2_XLBO = kChunk + 16;
+#else
+constexpr uint32_t V2_XLBO = kChunk;
+#endif
+constexpr uint32_t V2H_XCH = 10 * V2_XLBO;                   // per warp [32 rows][K' 10 | V 10] fp32: attention exchange of one head
 constexpr uint32_t V2H_RED = V2H_XCH + 8 * 2560;             // float2 [2][128] LayerNorm partials / float [2][128] head partials
 constexpr uint32_t V2H_RGBM = V2H_RED + 2 * 128 * 8;         // float4 [112]: (r,g,b,mask) of the tile's (point, view) pairs
 constexpr uint32_t V2H_SIZE = V2H_RGBM + 112 * 16;
@@ -64,14 +74,14 @@ __host__ __device__ constexpr int view2_group_rows(int nv) {
 }
 __host__ __device__ constexpr int view2_points_per_tile(int nv) { return (128 / view2_group_rows(nv)) * (view2_group_rows(nv) / (nv + 1)); }
 
-// K loop of an SS-form GEMM (A: 128-row K-major tile at a_base, B: K-major weight tile with b_rows rows at b_base) with the descriptors
+// K loop of an SS-form GEMM (A: the 128-row K-major token tile at a_base, chunk stride V2_XLBO; B: K-major weight tile with b_rows rows at b_base) with the descriptors
 // advanced by one 32-bit add per K step (ufo_umma.cuh: desc_lo / desc_hi)
 __device__ __forceinline__ void issue_gemm_lh(uint32_t tmem_d, uint32_t a_base, uint32_t b_base, uint32_t b_rows, uint32_t k_chunks,
                                               uint32_t idesc, uint32_t acc_first) {
-  const uint32_t a0 = umma::desc_lo(a_base, kChunk), b0 = umma::desc_lo(b_base, b_rows * 16u);
+  const uint32_t a0 = umma::desc_lo(a_base, V2_XLBO), b0 = umma::desc_lo(b_base, b_rows * 16u);
 #pragma unroll
   for (uint32_t c = 0; c < k_chunks; c += 2)
-    umma::mma_f16_lh(tmem_d, a0 + c * (kChunk >> 4), umma::desc_hi(128u), b0 + c * b_rows, umma::desc_hi(128u), idesc, (c > 0) ? 1u : acc_first);
+    umma::mma_f16_lh(tmem_d, a0 + c * (V2_XLBO >> 4), umma::desc_hi(128u), b0 + c * b_rows, umma::desc_hi(128u), idesc, (c > 0) ? 1u : acc_first);
 }
 // K loop of a TS-form GEMM: A chunk pairs from the TMEM columns a_col(ks), B K-major weight tile (b_rows rows) from K step k0 on
 template <typename ACol>
@@ -177,7 +187,7 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
     float v[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = (ln < RPW && (ln % L) == 0) ? prm.vtok[c * 8 + k] : 0.f;
-    st_chunk<BF16>(smem + V2_HALF + hb * V2H_SIZE + V2H_X, rr, c, v);
+    *reinterpret_cast<uint4*>(smem + V2_HALF + hb * V2H_SIZE + V2H_X + c * V2_XLBO + rr * 16) = pack8<BF16>(v);
   }
   umma::fence_async_smem();
   umma::tc_fence_before();
@@ -197,9 +207,22 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
   const int tstep = 2 * gridDim.x;
   auto slot_of = [&](int p) -> int { return (p >> 6) * kNS + half * kNC + (p & 63); };
 
-  // token rows of a tile -> X[buf] by cp.async: piece i = (row rr, chunk c); rows of the view token stay as initialised
+  // token rows of a tile -> X by cp.async; rows of the view token stay as initialised
   auto load_tokens = [&](int tile) {
     const int pbase = tile * PPT;
+#ifdef UFO_VIEW_TOK_CONTIG
+    constexpr int PIECES = PPT * NV * 10;                  // 16-byte pieces of the tile's token block: point-major, then view, then chunk
+#pragma unroll
+    for (int k = 0; k < (PIECES + 255) / 256; ++k) {
+      const int j = t + k * 256;
+      const int pp = j / (NV * 10), w = j - pp * (NV * 10);
+      const int v = w / 10, c = w - v * 10;
+      const int p = pbase + pp;
+      const int rr = (pp / PPW) * GR + (pp % PPW) * L + v + 1;
+      if (j < PIECES && p < P)
+        cp_async16(x_base + c * V2_XLBO + rr * 16, tok + (size_t)slot_of(p) * (NV * kDView) + w * 8);
+    }
+#else
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
       const int i = t + k * 256;
@@ -211,6 +234,7 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
         cp_async16(x_base + c * kChunk + rr * 16,
                    tok + (size_t)slot_of(p) * (NV * kDView) + (ll - 1) * kDView + c * 8);
     }
+#endif
     cp_async_commit();
   };
   // wait for this half's last commit: with UFO_VIEW_POLL1 one warp polls the mbarrier and releases the others through the

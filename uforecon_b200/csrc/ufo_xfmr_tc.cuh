@@ -318,6 +318,7 @@ __global__ void __launch_bounds__(256, UFO_GATHER_MINB) k_gather_tc(SceneDev sc,
     for (int i = threadIdx.x; i < 32 * 16; i += 256) s_w[o_w4 + i] = __ldg(presim.w4 + i);
     for (int i = threadIdx.x; i < 16; i += 256) s_w[o_b4 + i] = __ldg(presim.b4 + i);
   }
+  __syncthreads();        // the weights are read after the gather rounds, which end in a warp-level barrier only (below)
   const int sub = threadIdx.x >> 3, j = threadIdx.x & 7;
   const unsigned gmask = 0xFFu << (threadIdx.x & 24);
   const long long P = (long long)R * SN;
@@ -439,11 +440,14 @@ __global__ void __launch_bounds__(256, UFO_GATHER_MINB) k_gather_tc(SceneDev sc,
         }
       }
       const float sim = acc / (float)(NV * (NV - 1) / 2);
-      s_sim[round * 32 + sub][j] = sim;
+      s_sim[sub * 8 + round][j] = sim;                  // row sub * 8 + round: the 32 points of a warp are the 32 rows of ITS two MMA tiles
       if (sim8_out != nullptr) sim8_out[sl * 8 + j] = sim;
     }
   }
-  __syncthreads();
+  // A warp's MMA rows 32 w .. 32 w + 31 are the points it gathered itself (sub = 4 w .. 4 w + 3, eight rounds), so a warp-level barrier
+  // is enough here; with rows in point order (round * 32 + sub) this was a block-wide barrier at which the warps of a block waited for
+  // the slowest one's last gather round (8 % of the kernel's stall samples).
+  __syncwarp();
   // ---- pre_sim_mlp 8 -> 32 -> 32 -> 16 (ray_transformer.py:128-132) for the block's 256 points on the tensor cores: warp-level
   //      mma.sync m16n8k16 (16-bit operands, fp32 accumulate, biases as the initial accumulator).  A warp owns 32 points = two
   //      16-row tiles; the accumulator fragment of one layer IS the A fragment of the next (rows g / g+8, column pairs 2t), so the
@@ -535,7 +539,8 @@ __global__ void __launch_bounds__(256, UFO_GATHER_MINB) k_gather_tc(SceneDev sc,
         lo.z = __shfl_sync(0xffffffffu, v0, qb + 2); lo.w = __shfl_sync(0xffffffffu, v0, qb + 3);
         hi.x = __shfl_sync(0xffffffffu, v1, qb);     hi.y = __shfl_sync(0xffffffffu, v1, qb + 1);
         hi.z = __shfl_sync(0xffffffffu, v1, qb + 2); hi.w = __shfl_sync(0xffffffffu, v1, qb + 3);
-        const long long p = p0 + (hr ? r1 : r0);
+        const int row = hr ? r1 : r0;                                    // row = sub * 8 + round of point p0 + round * 32 + sub
+        const long long p = p0 + (row & 7) * 32 + (row >> 3);
         if (p < P) {
           const size_t sl = (size_t)tc_slot(p, half);
 #pragma unroll
