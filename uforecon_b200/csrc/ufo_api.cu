@@ -298,6 +298,16 @@ static int tc_weights_build(const UfoWeightsDesc* d, TcWeights* t, cudaStream_t 
   memcpy(vp.rb2, d->radiance.b2, 32);
   memcpy(vp.rw4, d->radiance.w4, 32);
   vp.rb4 = d->radiance.b4[0];
+  for (int j = 0; j < 80; ++j) {      // view-token row of the QKV GEMM with the fp16 operands of the tensor-core path, accumulated in double
+    double k = 0.0, v = 0.0;
+    for (int c = 0; c < 80; ++c) {
+      const double x = back16(cvt16(d->view_token[c], false), false);
+      k += x * back16(cvt16(d->view.k[j * 80 + c], false), false);
+      v += x * back16(cvt16(d->view.v[j * 80 + c], false), false);
+    }
+    vp.k0[j] = (float)(k > 0.0 ? k + 1.0 : exp(k));
+    vp.v0[j] = (float)v;
+  }
   RayParams& rp = t->rp;
   memcpy(rp.n1w, d->ray.norm1_w, 352); memcpy(rp.n1b, d->ray.norm1_b, 352);
   memcpy(rp.n2w, d->ray.norm2_w, 352); memcpy(rp.n2b, d->ray.norm2_b, 352);

@@ -21,6 +21,7 @@
 // r_hi [96,144) r_lo [144,192) | SRDF-head accumulator [0,32).
 #pragma once
 #include "ufo_view_tc2.cuh"
+#include <cstdio>
 
 namespace ufo {
 namespace tc {
@@ -41,7 +42,11 @@ constexpr uint32_t R2_SCR = R2_V + 96 * 96 * 2;            // LayerNorm / SRDF p
 constexpr uint32_t R2_SLOT = R2_V + 12 * kChunk;           // two weight slots
 constexpr uint32_t R2_SLOT_BYTES = 176 * 96 * 2;           // 33,792: the largest piece
 constexpr uint32_t R2_BAR = R2_SLOT + 2 * R2_SLOT_BYTES;
+#ifdef UFO_PHASE_TIMING                                     // debug build: per-phase clock64 sums of one warp, printed by block 0
+constexpr uint32_t R2_SMEM = R2_BAR + 64 + 256;
+#else
 constexpr uint32_t R2_SMEM = R2_BAR + 64;
+#endif
 static_assert(R2_SMEM <= 115712, "ray-stage (v2) shared memory: two CTAs must fit one SM");
 static_assert(R2_SCR + 2 * 128 * 8 <= R2_SLOT, "scratch overlaps the weight slots");
 }  // namespace tc
@@ -217,45 +222,56 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     asm volatile("" : "+r"(pv));
     return prow < P ? tile * 128 + (long long)pv : -1;
   };
-  // 16 bytes of read-only global memory, or zeros: ONE predicated load, no branch.  (As `if (ok) v = __ldg(p)` under the row / chunk
-  // conditions the twelve loads of a row sat in four conditional blocks, and the warp waited for the loads already in flight at every
-  // one of those branches: 15 % of the kernel's stall samples were in x_issue, more than in the MMA waits it is meant to hide under.)
-  auto ldg4_pred = [](const float* ptr, bool ok) -> float4 {
-    float4 v;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %5, 0;\n\t"
-        "mov.f32 %0, 0f00000000;\n\t"
-        "mov.f32 %1, 0f00000000;\n\t"
-        "mov.f32 %2, 0f00000000;\n\t"
-        "mov.f32 %3, 0f00000000;\n\t"
-        "@p ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t"
-        "}"
-        : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-        : "l"(ptr), "r"((int)ok));
-    return v;
-  };
   // This thread's half of the fp32 input row, chunks 6 g .. 6 g + 5: view-stage output (chunks 0..9), order encoding (chunk 10,
-  // ray_transformer.py:301-303), zero (chunk 11).  The loads are ISSUED ahead of an MMA wait and consumed after it, so that their L2
-  // latency is not exposed; straight-line code, the column half g only selects addresses and predicates.
-  float4 xr[12];
-  auto x_issue = [&](long long ir) {
+  // ray_transformer.py:301-303), zero (chunk 11).  A tile needs it twice (three times with two sequences): as the 16-bit operand of
+  // R0 (and of mlp.0 when x was overwritten in TMEM) and in fp32 as the residual of R12.  It is copied global -> SHARED memory by
+  // cp.async (x_copy) and read from there (x_get): no registers are held while the copy is in flight and no scoreboard of the warp is
+  // tied to it.  As register loads issued "under" an MMA wait (the first version) the warp could not leave that wait before its loads
+  // had landed: measured with per-phase clocks, the two waits that carried the loads took 2180 and 2990 cycles where the others take
+  // 850-1050 (12 % of a tile).  The stash is the K' / V' operand area, dead between the message GEMM (R5) and the next tile's R2a:
+  //   piece j (16 bytes) of thread (r, g = 0): R2_K + j * 2048 + r * 16, j < 12;   (r, g = 1): R2_K + 24576 + j * 2048 + r * 16, j < 8
+  // (ends at R2_SCR; a thread only reads what it copied itself, so cp.async.wait_group is all the synchronisation it needs).
+  static_assert(R2_K + 24576 + 8 * 2048 <= R2_SCR, "x stash overlaps the scratch");
+  const uint32_t xs_u32 = sm_base + R2_K + (g ? 24576u : 0u) + (uint32_t)r * 16u;
+  const float4* const xs_ptr = reinterpret_cast<const float4*>(smem + R2_K + (g ? 24576 : 0) + r * 16);
+  auto x_copy = [&](long long ir) {
     const bool ok = ir >= 0;
     const float* src = vout0 + (size_t)(ok ? ir : 0) * kDView + 48 * g;      // chunk 6 g of the row
-    const float* pe = pe_table + (r % SN) * 8;
+    const uint32_t nbytes = ok ? 16u : 0u;                                   // rows past P: zero fill
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {                                            // chunks 0..3 | 6..9
-      xr[2 * i] = ldg4_pred(src + 8 * i, ok);
-      xr[2 * i + 1] = ldg4_pred(src + 8 * i + 4, ok);
+    for (int j = 0; j < 12; ++j)
+      if (j < 8 || g == 0)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(xs_u32 + j * 2048u), "l"(src + 4 * j), "r"(nbytes) : "memory");
+    cp_async_commit();
+  };
+  float4 xr[12];
+  auto x_get = [&]() {                                                       // after cp_async_wait_all()
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xr[j] = xs_ptr[j * 128];
+    if (g == 0) {
+#pragma unroll
+      for (int j = 8; j < 12; ++j) xr[j] = xs_ptr[j * 128];
+    } else {
+      const float4* pe = reinterpret_cast<const float4*>(pe_table + (r % SN) * 8);
+      xr[8] = __ldg(pe);
+      xr[9] = __ldg(pe + 1);
+      xr[10] = xr[11] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    const float* p4 = g ? pe : src + 32;                                     // chunk 4 | 10 (order encoding)
-    const bool ok4 = g ? true : ok;
-    xr[8] = ldg4_pred(p4, ok4);
-    xr[9] = ldg4_pred(p4 + 4, ok4);
-    const bool ok5 = ok && g == 0;                                           // chunk 5 | 11 (zero)
-    xr[10] = ldg4_pred(src + 40, ok5);
-    xr[11] = ldg4_pred(src + 44, ok5);
+  };
+  // the next tile's rows of vout0 -> L2, one tile ahead of the copy that reads them (they come from DRAM: the view stage wrote 1.5 GB)
+  auto x_prefetch = [&](long long tile_nx) {
+    if (SN == kNC) {                                                         // two rays per tile: 64 rows of 320 bytes each
+      const long long ray = tile_nx * 2 + (t >> 7);
+      if (ray * kNC < P) {
+        const char* base = reinterpret_cast<const char*>(vout0 + (size_t)ray * kNS * kDView);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (t & 127) * 128));
+        if ((t & 127) < 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (128 + (t & 127)) * 128));
+      }
+    } else {                                                                 // one ray: 128 contiguous rows
+      const char* base = reinterpret_cast<const char*>(vout0 + (size_t)tile_nx * kNS * kDView);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(base + t * 128));
+      if (t < 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (256 + t) * 128));
+    }
   };
   // the loaded chunks as 16-bit operand chunks -> TMEM columns col0 + 4 c   (n_chunks: 12 for the QKV operand, 11 for [LN1 | x])
   auto x_store = [&](uint32_t col0, int n_chunks) {
@@ -268,19 +284,37 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     }
   };
   long long in_row_cur = (long long)blockIdx.x < n_tiles ? in_row_from(blockIdx.x, perm_load(blockIdx.x)) : -1;
-  if ((long long)blockIdx.x < n_tiles) x_issue(in_row_cur);
+  if ((long long)blockIdx.x < n_tiles) x_copy(in_row_cur);
 
+#ifdef UFO_PHASE_TIMING
+  // interval k of a tile ends at the k-th UFO_TIM(): even k = a barrier in front of an MMA issue (epilogue + barrier), odd k = the return
+  // of the MMA wait (issue + MMA + commit + wake-up); timed by lane 0 of warp 1 (not the issuing warp, column half g = 0)
+  unsigned long long* tim = reinterpret_cast<unsigned long long*>(smem + R2_BAR + 64);
+  if (t == 32) for (int i = 0; i < 32; ++i) tim[i] = 0;
+  long long tim_prev = clock64();
+  int tim_idx = 0;
+#define UFO_TIM() do { if (t == 32) { const long long now_ = clock64(); tim[tim_idx] += (unsigned long long)(now_ - tim_prev); tim_prev = now_; } ++tim_idx; } while (0)
+#else
+#define UFO_TIM() do { } while (0)
+#endif
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+#ifdef UFO_PHASE_TIMING
+    tim_idx = 0;
+#endif
     const long long prow = tile * 128 + r;           // this thread's token: ray prow / SN, sorted sample prow % SN
     const bool row_ok = prow < P;
     const long long in_row = in_row_cur;             // looked up one tile ahead (in_row_nx of the previous iteration)
     const bool has_next = tile + (long long)gridDim.x < n_tiles;
     const unsigned pv_nx = has_next ? perm_load(tile + gridDim.x) : 0u;         // the next tile's perm byte: used in R13
+    if (has_next) x_prefetch(tile + gridDim.x);
     // ---- R0: x = [view-stage token 0 output | order encoding | 0] -> 16-bit A operand in TMEM (chunks 6 g .. 6 g + 5)
-    x_store(C_X, 12);                                            // loads issued by the previous tile (or the prologue)
+    cp_async_wait_all();                                         // copy issued by the previous tile's R13 (or the prologue)
+    x_get();
+    x_store(C_X, 12);
     umma::tmem_st_wait();
     umma::tc_fence_before();
     __syncthreads();
+    UFO_TIM();
     // ---- R1a: k | v = x . Wkv^T
     const uint32_t b1 = use_piece();
     if (UFO_RAY_ISSUE_WARP) {
@@ -297,6 +331,7 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     }
     first_gemm = false;
     mma_wait();
+    UFO_TIM();
     load_piece(2);                                   // merge weights -> the slot Wkv leaves
     // ---- R2a: K' = elu(k)+1, V' = v -> MN-major operand tiles in shared memory   (linear_attention.py:36-41)
     {
@@ -323,6 +358,7 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     umma::fence_async_smem();
     umma::tc_fence_before();
     __syncthreads();
+    UFO_TIM();
     // ---- R1b: q = x . Wq^T   (the k | v accumulator is consumed)
     const uint32_t b2 = use_piece();
     if (UFO_RAY_ISSUE_WARP) {
@@ -336,6 +372,7 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
       }
     }
     mma_wait();
+    UFO_TIM();
     load_piece(3);                                   // mlp.0 rows 0..95
     // ---- R2b: Q' = elu(q)+1 -> A operand of the message GEMM (chunk 11 = 0)
     {
@@ -359,6 +396,7 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     }
     umma::tc_fence_before();
     __syncthreads();
+    UFO_TIM();
     // ---- R3: per sequence  D[b][a] = sum_s V'[s][b] K'[s][a]   (rows 88..95 = sum_s K'[s][a]);  both operands MN-major
     if (UFO_RAY_ISSUER) {
       umma::tc_fence_after();
@@ -375,6 +413,7 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
       umma::commit(bar);
     }
     mma_wait();
+    UFO_TIM();
     // ---- R4: block-diagonal KV (per head 11x11) + per-head K-sum rows as the B operand of the message GEMM
     if (r < 96) {
       const int hr = r < 88 ? r / 11 : r - 88;       // rows 0..87: KV_h of the row's head; row 88+h: the K-sum of head h
@@ -401,6 +440,7 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     umma::fence_async_smem();
     umma::tc_fence_before();
     __syncthreads();
+    UFO_TIM();
     // ---- R5: message numerator Q'.KV_h (columns 0..87) and per-head normalisers Q'_h.Ksum_h (columns 88..95)
     if (UFO_RAY_ISSUER) {
       umma::tc_fence_after();
@@ -409,6 +449,8 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
       umma::commit(bar);
     }
     mma_wait();
+    UFO_TIM();
+    x_copy(in_row);                                              // K' / V' / KV are dead: this tile's x again -> stash (for R8 / R12), an L2 hit
     // ---- R6: msg = numerator / (normaliser + 1e-6)                (linear_attention.py:44-45) -> A operand of the merge
     {
       const uint32_t dm = tl + ((NSEQ == 1 || r < SN) ? D_S0 : D_S1);
@@ -438,6 +480,7 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     }
     umma::tc_fence_before();
     __syncthreads();
+    UFO_TIM();
     // ---- R7: merge
     const uint32_t b3 = use_piece();
     if (UFO_RAY_ISSUE_WARP) {
@@ -450,8 +493,8 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
         commit_and_prewait(true);
       }
     }
-    if (NSEQ > 1) x_issue(in_row);                               // x again, for the [LN1 | x] operand: under the merge GEMM
     mma_wait();
+    UFO_TIM();
     load_piece(4);                                   // mlp.0 rows 96..175
     // ---- R8: LayerNorm 1 -> first half of the concat operand [LN1 | x] (chunks 0..10; the weight image has the same K order)
     {
@@ -463,7 +506,11 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
         for (int i = 0; i < NC; ++i) tmem_ld8p(tl + D_MRG + 8 * (C0 + i), v[i]);
         umma::tmem_ld_wait();
         red[GG * 128 + r] = ln_partial<NC>(v);
-        if (NSEQ > 1) x_store(C_XL + 44, 11);
+        if (NSEQ > 1) {                                           // x again, for the [LN1 | x] operand
+          cp_async_wait_all();
+          x_get();
+          x_store(C_XL + 44, 11);
+        }
         umma::tc_fence_before();
         pair_sync();                                               // the partials of a row come from the warps q and q + 4 only
         const float2 st = ln2_stats(red, r, 1.f / 88.f);
@@ -480,6 +527,7 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     }
     umma::tc_fence_before();
     __syncthreads();
+    UFO_TIM();
     // ---- R9a: mlp.0 on [LN1 | x]  (K = 176), output rows 0..95
     const uint32_t b4 = use_piece();
     if (UFO_RAY_ISSUE_WARP) {
@@ -493,6 +541,7 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
       }
     }
     mma_wait();
+    UFO_TIM();
     load_piece(5);                                   // mlp.2
     // ---- R10a: ReLU -> hidden operand chunks 0..11
     {
@@ -512,6 +561,7 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     }
     umma::tc_fence_before();
     __syncthreads();
+    UFO_TIM();
     // ---- R9b: mlp.0 output rows 96..175 (the first accumulator is consumed)
     const uint32_t b5 = use_piece();
     if (UFO_RAY_ISSUE_WARP) {
@@ -524,8 +574,8 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
         commit_and_prewait(true);
       }
     }
-    x_issue(in_row);                                             // fp32 residual input of R12: two GEMMs ahead of its use
     mma_wait();
+    UFO_TIM();
     load_piece(6);                                   // SRDF head layer 0 (hi | lo)
     // ---- R10b: ReLU -> hidden operand chunks 12..21 (over the dead [LN1 | x] operand)
     {
@@ -545,6 +595,7 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     }
     umma::tc_fence_before();
     __syncthreads();
+    UFO_TIM();
     // ---- R11: mlp.2
     const uint32_t b6 = use_piece();
     if (UFO_RAY_ISSUE_WARP) {
@@ -558,6 +609,7 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
       }
     }
     mma_wait();
+    UFO_TIM();
     if (has_next) load_piece(0);                       // the next tile's Wkv
     // ---- R12: LayerNorm 2, residual in fp32 from the fp32 input, split hi/lo for the SRDF head
     {
@@ -571,6 +623,8 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
         red[GG * 128 + r] = ln_partial<NC>(v);
         umma::tc_fence_before();
         pair_sync();
+        cp_async_wait_all();
+        x_get();                                                   // fp32 input row from the stash (copied at R6)
         const float2 st = ln2_stats(red, r, 1.f / 88.f);
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
@@ -602,6 +656,7 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     }
     umma::tc_fence_before();
     __syncthreads();
+    UFO_TIM();
     // ---- R13: DensityMLP layer 0 in split precision: r_hi.W_hi + r_lo.W_hi + r_hi.W_lo   (ray_transformer.py:147-150)
     const uint32_t b7 = use_piece();
     if (UFO_RAY_ISSUE_WARP) {
@@ -617,9 +672,10 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
       }
     }
     const long long in_row_nx = has_next ? in_row_from(tile + gridDim.x, pv_nx) : -1;
-    if (has_next) x_issue(in_row_nx);                            // the next tile's x: under the SRDF-head GEMM and its tail
+    if (has_next) x_copy(in_row_nx);                             // the next tile's x: under the SRDF-head GEMM and its tail
     in_row_cur = in_row_nx;
     mma_wait();
+    UFO_TIM();
     if (has_next) load_piece(1);                       // the next tile's Wq
     // ---- R14: DensityMLP tail 32 -> 16 -> 1 in fp32 (hidden units 8 g .. 8 g + 7 per thread)
     {
@@ -650,6 +706,15 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     }
     // the scratch is rewritten by the next tile's R2a only after its R0 barrier; TMEM is rewritten after that barrier too
   }
+#ifdef UFO_PHASE_TIMING
+  if (blockIdx.x == 0 && t == 32 && n_tiles >= 4096) {
+    const unsigned long long nt = (unsigned long long)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+    printf("RAYTIM SN=%d tiles=%llu :", SN, nt);
+    for (int i = 0; i < 18; ++i) printf(" %llu", tim[i] / nt);
+    printf("\n");
+  }
+#endif
+#undef UFO_TIM
   umma::tc_fence_before();
   __syncthreads();
   if (wl == 0) umma::tmem_dealloc(tm, 256);

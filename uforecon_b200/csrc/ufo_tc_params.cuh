@@ -15,6 +15,9 @@ constexpr uint32_t kChunk = 2048;   // bytes of one 8-column chunk of a 128-row 
 struct ViewParams {
   float n1w[80], n1b[80], n2w[80], n2b[80], vtok[80];
   float rb0[16], rw0d[16][3], rw2[8][16], rb2[8], rw4[8], rb4;
+  // K' = elu(k) + 1 and V of the view-token row (transformer.py:47, linear_attention.py:36-37 applied to view_token): the same for every
+  // sample point, evaluated once on the host from the fp16-rounded operands the QKV GEMM sees (k_view_tc2, fp16 mode)
+  float k0[80], v0[80];
 };
 
 namespace tc {

@@ -29,6 +29,7 @@
 // mlp.2 accumulator [80,160), LN2 + direction/bias operand [0,24) [24,48).
 #pragma once
 #include "ufo_xfmr_tc.cuh"
+#include <cstdio>
 
 namespace ufo {
 namespace tc {
@@ -56,7 +57,11 @@ constexpr uint32_t V2H_RGBM = V2H_RED + 2 * 128 * 8;         // float4 [112]: (r
 constexpr uint32_t V2H_SIZE = V2H_RGBM + 112 * 16;
 constexpr uint32_t V2_HALF = V2_WEND;
 constexpr uint32_t V2_BAR = V2_HALF + 2 * V2H_SIZE;
+#ifdef UFO_PHASE_TIMING                                     // debug build: per-phase clock64 sums of one warp of half 0, printed by block 0
+constexpr uint32_t V2_SMEM = V2_BAR + 64 + 256;
+#else
 constexpr uint32_t V2_SMEM = V2_BAR + 64;
+#endif
 static_assert(V2_SMEM <= 232448, "view-stage (v2) shared memory exceeds the 227 KB opt-in limit");
 
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
@@ -294,7 +299,20 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
     }
   };
   int prev_pbase = -1;
+#ifdef UFO_PHASE_TIMING
+  unsigned long long* tim = reinterpret_cast<unsigned long long*>(smem + V2_BAR + 64);
+  if (tid == 32) for (int i = 0; i < 32; ++i) tim[i] = 0;
+  long long tim_prev = clock64();
+  int tim_idx = 0, tim_tiles = 0;
+#define UFO_TIM() do { if (tid == 32) { const long long now_ = clock64(); tim[tim_idx] += (unsigned long long)(now_ - tim_prev); tim_prev = now_; } ++tim_idx; } while (0)
+#else
+#define UFO_TIM() do { } while (0)
+#endif
   for (; tile < n_tiles; tile += tstep) {
+#ifdef UFO_PHASE_TIMING
+    tim_idx = 0;
+    ++tim_tiles;
+#endif
     const int pbase = tile * PPT;
     const int my_p = pbase + pl;
     const size_t my_slot = (size_t)slot_of(my_p);
@@ -305,6 +323,7 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
     umma::fence_async_smem();
     umma::tc_fence_before();
     umma::bar_sync(bar_id, 256);
+    UFO_TIM();
     // ---- P1: q|k|v = X . Wqkv^T (transformer.py:47) and the x part of the radiance head's first layer
     if (UFO_VIEW_ISSUER) {
       umma::tc_fence_after();
@@ -329,10 +348,17 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
     if (prev_pbase >= 0) blend(prev_pbase);                      // the previous tile's colours, under this tile's QKV GEMM
 #endif
     half_wait();
+    UFO_TIM();
     // ---- P2+P3: elu+1 on q, k; msg_l = sum_s (Q_l.K_s) V_s / (sum_s Q_l.K_s + 1e-6) per head over the L token rows of
     //      the point (== Q (K^T V) Z, linear_attention.py:36-45), K'/V' of the other rows by warp shuffle.
     //      Thread (row, g) owns heads 4g .. 4g+3 = columns [120g, 120g+120) of the accumulator.
+    //      The view-token row (s = 0) of every point is the same constant input, so its K' and V are constants of the weights: they come
+    //      from the parameter block (ViewParams::k0 / v0, computed on the host from the same 16-bit operands), not through the exchange
+    //      buffer - a quarter of the phase's LDS.128 at NV = 3.  The phase is bound by the shared-memory pipe (58 % busy over the whole
+    //      kernel, 6400 of the 14 900 cycles of a tile by per-phase clocks).  -DUFO_VIEW_TOK0_SMEM: every row through the buffer.
     {
+      auto attn = [&](auto GGc) {
+      constexpr int GG = decltype(GGc)::value;
       uint32_t mo[24];
 #pragma unroll
       for (int hp = 0; hp < 2; ++hp) {
@@ -367,8 +393,22 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
           float den = 0.f;
 #pragma unroll
           for (int s = 0; s < L; ++s) {
-            const float4* src = xw + ((sl0 + s) & (GR - 1)) * 5;   // the same address for the L rows of a point: broadcast
-            const float4 a0 = src[0], a1 = src[1], a2 = src[2], a3 = src[3], a4 = src[4];
+            float4 a0, a1, a2, a3, a4;
+#ifndef UFO_VIEW_TOK0_SMEM
+            if (s == 0) {                                          // the view-token row: constants
+              const float* kc = prm.k0 + 40 * GG + 20 * hp + 10 * hh;
+              const float* vc = prm.v0 + 40 * GG + 20 * hp + 10 * hh;
+              a0 = make_float4(kc[0], kc[1], kc[2], kc[3]);
+              a1 = make_float4(kc[4], kc[5], kc[6], kc[7]);
+              a2 = make_float4(kc[8], kc[9], vc[0], vc[1]);
+              a3 = make_float4(vc[2], vc[3], vc[4], vc[5]);
+              a4 = make_float4(vc[6], vc[7], vc[8], vc[9]);
+            } else
+#endif
+            {
+              const float4* src = xw + ((sl0 + s) & (GR - 1)) * 5;   // the same address for the L rows of a point: broadcast
+              a0 = src[0]; a1 = src[1]; a2 = src[2]; a3 = src[3]; a4 = src[4];
+            }
             float2 acc = __fmul2_rn(q2[5 * hh], make_float2(a0.x, a0.y));
             acc = __ffma2_rn(q2[5 * hh + 1], make_float2(a0.z, a0.w), acc);
             acc = __ffma2_rn(q2[5 * hh + 2], make_float2(a1.x, a1.y), acc);
@@ -395,9 +435,12 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
       umma::tmem_st8(tl + G + 8, mo + 8);
       umma::tmem_st8(tl + G + 16, mo + 16);
       umma::tmem_st_wait();
+      };
+      UFO_G2_DISPATCH(attn)
     }
     umma::tc_fence_before();
     umma::bar_sync(bar_id, 256);
+    UFO_TIM();
     // ---- P4: merge (transformer.py:55), A from TMEM
     if (UFO_VIEW_ISSUER) {
       umma::tc_fence_after();
@@ -407,6 +450,7 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
     }
     if (t < PPT * NV) s_rgbm[t] = my_col;
     half_wait();
+    UFO_TIM();
     // ---- P5: LayerNorm 1 (transformer.py:56) -> message half of the mlp.0 operand, columns [24g, 24g+24)
     {
       auto ln1 = [&](auto GGc) {
@@ -438,6 +482,7 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
     }
     umma::tc_fence_before();
     umma::bar_sync(bar_id, 256);
+    UFO_TIM();
     // ---- P6: mlp.0 on [x | LN1]  (transformer.py:57): message half from TMEM on top of the x half issued inside P5
     if (UFO_VIEW_ISSUER) {
       umma::tc_fence_after();
@@ -446,6 +491,7 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
       umma::commit(bar);
     }
     half_wait();
+    UFO_TIM();
     if (tile + tstep < n_tiles) load_tokens(tile + tstep);     // X is free: mlp.0 was the last MMA reading it
     // ---- P7: ReLU -> hidden operand [40g, 40g+40)
     {
@@ -468,6 +514,7 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
     }
     umma::tc_fence_before();
     umma::bar_sync(bar_id, 256);
+    UFO_TIM();
     // ---- P8: mlp.2
     if (UFO_VIEW_ISSUER) {
       umma::tc_fence_after();
@@ -475,6 +522,7 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
       umma::commit(bar);
     }
     half_wait();
+    UFO_TIM();
     // ---- P9: LayerNorm 2; token 0: out = view_token + LN2 -> vout0 (fp32); view rows: LN2 (+ direction, 1) -> operand of the
     //      radiance head (x + LN2 is applied inside the head's GEMM: W0x.x + W0x.LN2)
     {
@@ -515,6 +563,7 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
     }
     umma::tc_fence_before();
     umma::bar_sync(bar_id, 256);
+    UFO_TIM();
     // ---- P10: LN2 / direction / bias part of the radiance head's first layer   (ray_transformer.py:159-163,313)
     if (UFO_VIEW_ISSUER) {
       umma::tc_fence_after();
@@ -523,6 +572,7 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
       umma::commit(bar);
     }
     half_wait();
+    UFO_TIM();
     // ---- P11: head tail 16 -> 8 -> 1 (hidden units 4g .. 4g+3 per thread), masked softmax over views, colour blend
     {
       float h[16];
@@ -551,6 +601,7 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
 #ifdef UFO_VIEW_BLEND_INLINE
     umma::tc_fence_before();
     umma::bar_sync(bar_id, 256);
+    UFO_TIM();
     blend(pbase);
 #else
     prev_pbase = pbase;         // blended after the next P0 barrier, which also publishes omg
@@ -558,6 +609,14 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
     // omg / s_rgbm are next written after several more barriers of this half; the next tile's QKV MMA overwrites TMEM only
     // after its P0 barrier, which every thread reaches after its last TMEM read above
   }
+#ifdef UFO_PHASE_TIMING
+  if (blockIdx.x == 0 && tid == 32 && n_tiles >= 4096) {
+    printf("VIEWTIM NV=%d tiles=%d :", NV, tim_tiles);
+    for (int i = 0; i < 12; ++i) printf(" %llu", tim[i] / (unsigned long long)tim_tiles);
+    printf("\n");
+  }
+#endif
+#undef UFO_TIM
   cp_async_wait_all();
 #ifndef UFO_VIEW_BLEND_INLINE
   if (prev_pbase >= 0) {                                         // the last tile of this half
