@@ -174,6 +174,16 @@ static void pack_b(uint8_t* img, const float* W, int n_real, int k_real, int ldw
     }
 }
 
+// K columns k0 .. k0+79 of W [rows][ldw] moved to the channel order of the 16-bit token rows: out[., k0 + tok_pos(c)] = W[., k0 + c]
+static void permute_tok_cols(float* W, int rows, int ldw, int k0) {
+  float tmp[80];
+  for (int o = 0; o < rows; ++o) {
+    float* w = W + (size_t)o * ldw + k0;
+    for (int c = 0; c < 80; ++c) tmp[tok_pos(c)] = w[c];
+    memcpy(w, tmp, sizeof(tmp));
+  }
+}
+
 // byte offsets of the k_view_tc2 weight image (mirrors tc::V2_W* in ufo_view_tc2.cuh, which only device TUs include)
 constexpr size_t kV2WQkv = 0, kV2WMrg = kV2WQkv + 240 * 80 * 2, kV2WMl0 = kV2WMrg + 80 * 96 * 2, kV2WMl2 = kV2WMl0 + 160 * 176 * 2,
                  kV2WRad = kV2WMl2 + 80 * 160 * 2, kV2WEnd = kV2WRad + 16 * 176 * 2;
@@ -194,9 +204,12 @@ static int tc_weights_build(const UfoWeightsDesc* d, TcWeights* t, cudaStream_t 
       memcpy(qkv.data(), d->view.q, sizeof(float) * 6400);
       memcpy(qkv.data() + 6400, d->view.k, sizeof(float) * 6400);
       memcpy(qkv.data() + 12800, d->view.v, sizeof(float) * 6400);
+      permute_tok_cols(qkv.data(), 240, 80, 0);
       pack_b(vi.data() + tc::V_WQKV, qkv.data(), 240, 80, 80, 240, 80, bf16);
       pack_b(vi.data() + tc::V_WMRG, d->view.merge, 80, 80, 80, 80, 80, bf16);
-      pack_b(vi.data() + tc::V_WML0, d->view.mlp0, 160, 160, 160, 160, 160, bf16);
+      std::vector<float> ml0p(d->view.mlp0, d->view.mlp0 + 160 * 160);
+      permute_tok_cols(ml0p.data(), 160, 160, 0);
+      pack_b(vi.data() + tc::V_WML0, ml0p.data(), 160, 160, 160, 160, 160, bf16);
       pack_b(vi.data() + tc::V_WML2, d->view.mlp2, 80, 160, 160, 80, 160, bf16);
       // [W0x | W0x | W0dir b0 0..]: the head sees x + LN2 without forming the sum; direction and bias ride in two
       // extra K chunks of the operand (columns 160..162 = relative direction, 163 = 1)
@@ -206,6 +219,7 @@ static int tc_weights_build(const UfoWeightsDesc* d, TcWeights* t, cudaStream_t 
         for (int k = 0; k < 3; ++k) rad[o * 176 + 160 + k] = d->radiance.w0[o * 83 + 80 + k];
         rad[o * 176 + 163] = d->radiance.b0[o];
       }
+      permute_tok_cols(rad.data(), 16, 176, 0);
       pack_b(vi.data() + tc::V_WRAD, rad.data(), 16, 176, 176, 16, 176, bf16);
     }
     {  // ray stage
@@ -227,6 +241,7 @@ static int tc_weights_build(const UfoWeightsDesc* d, TcWeights* t, cudaStream_t 
       for (int g = 0; g < 2; ++g)
         for (int pt = 0; pt < 3; ++pt)
           for (int j = 0; j < 40; ++j) memcpy(qkv.data() + (size_t)(120 * g + 40 * pt + j) * 80, part[pt] + (size_t)(40 * g + j) * 80, sizeof(float) * 80);
+      permute_tok_cols(qkv.data(), 240, 80, 0);
       pack_b(v2.data() + kV2WQkv, qkv.data(), 240, 80, 80, 240, 80, bf16);
       // K = 80 message / LayerNorm channels as [g0: 40 | 8 zeros | g1: 40 | 8 zeros]
       auto pad96 = [](const float* W, int ldw, int col0, float* out, int ldo, int ocol0, int rows) {
@@ -242,6 +257,7 @@ static int tc_weights_build(const UfoWeightsDesc* d, TcWeights* t, cudaStream_t 
       std::vector<float> ml0((size_t)160 * 176);
       for (int o = 0; o < 160; ++o) memcpy(ml0.data() + (size_t)o * 176, d->view.mlp0 + (size_t)o * 160, sizeof(float) * 80);
       pad96(d->view.mlp0, 160, 80, ml0.data(), 176, 80, 160);
+      permute_tok_cols(ml0.data(), 160, 176, 0);
       pack_b(v2.data() + kV2WMl0, ml0.data(), 160, 176, 176, 160, 176, bf16);
       pack_b(v2.data() + kV2WMl2, d->view.mlp2, 80, 160, 160, 80, 160, bf16);
       // radiance head layer 0 on [x | LN2 g0 | dir 3, 1, 0.. | LN2 g1 | 0..]: x + LN2 without forming the sum, bias via the 1
@@ -252,6 +268,7 @@ static int tc_weights_build(const UfoWeightsDesc* d, TcWeights* t, cudaStream_t 
         for (int k = 0; k < 3; ++k) rad[(size_t)o * 176 + 80 + 40 + k] = d->radiance.w0[o * 83 + 80 + k];
         rad[(size_t)o * 176 + 80 + 43] = d->radiance.b0[o];
       }
+      permute_tok_cols(rad.data(), 16, 176, 0);
       pack_b(v2.data() + kV2WRad, rad.data(), 16, 176, 176, 16, 176, bf16);
       UFO_CUDA(cudaMalloc(&t->view_img2[f], v2.size()));
       UFO_CUDA(cudaMemcpyAsync(t->view_img2[f], v2.data(), v2.size(), cudaMemcpyHostToDevice, st));
@@ -291,6 +308,7 @@ static int tc_weights_build(const UfoWeightsDesc* d, TcWeights* t, cudaStream_t 
   memcpy(vp.n1w, d->view.norm1_w, 320); memcpy(vp.n1b, d->view.norm1_b, 320);
   memcpy(vp.n2w, d->view.norm2_w, 320); memcpy(vp.n2b, d->view.norm2_b, 320);
   memcpy(vp.vtok, d->view_token, 320);
+  for (int c = 0; c < 80; ++c) vp.vtok_x[tok_pos(c)] = d->view_token[c];
   memcpy(vp.rb0, d->radiance.b0, 64);
   for (int o = 0; o < 16; ++o)
     for (int i = 0; i < 3; ++i) vp.rw0d[o][i] = d->radiance.w0[o * 83 + 80 + i];
@@ -773,7 +791,7 @@ __global__ void k_tap_tokens(const uint16_t* __restrict__ tok, const uint8_t* __
   const long long p = pn / NV;
   const int n = (int)(pn % NV);
   const long long src = (p / kNS) * kNS + perm[p];
-  const uint32_t u = tok[(src * NV + n) * kDView + c];
+  const uint32_t u = tok[(src * NV + n) * kDView + tok_pos(c)];
   const float v = BF16 ? __uint_as_float(u << 16) : __half2float(__ushort_as_half((unsigned short)u));
   if (tokens) tokens[t] = v;
   if (vol24 && n == 0 && c >= 32 && c < 56) vol24[p * 24 + (c - 32)] = v;

@@ -16,6 +16,14 @@ constexpr int kFeatC = 32;   // FPN feature / match-map channels   (ray_transfor
 constexpr int kVolC = 8;     // CostRegNetWeight feature channels  (feature_volume.py:110)
 constexpr int kDView = 80;   // 32 + 24 + 16 + 8                   (ray_transformer.py:135)
 constexpr int kDRay = 88;    // kDView + 8 order PE                (ray_transformer.py:138)
+// Position of token channel c (reference order: feat 32 | vol 24 | sim 16 | depth PE 8, ray_transformer.py:258-288) inside the 16-bit
+// token rows of the tensor-core path.  The gather's lane j of a point owns feat 4j..4j+3, channel j of the three frustum features and
+// depth-PE component j: the row keeps those eight values adjacent ([lane 0: f f f f v0 v1 v2 pe | lane 1: ... ] | sim 16), so a lane
+// writes its part of a view row as ONE 16-byte store (it was one 8-byte and four 2-byte stores).  The K columns of every weight that
+// multiplies a token (QKV, the x half of mlp.0, the x part of the radiance head) are permuted the same way on the host.
+__host__ __device__ constexpr int tok_pos(int c) {
+  return c < 32 ? 8 * (c / 4) + c % 4 : (c < 56 ? 8 * ((c - 32) % 8) + 4 + (c - 32) / 8 : (c < 72 ? 64 + (c - 56) : 8 * (c - 72) + 7));
+}
 constexpr int kHeads = 8;
 constexpr int kNC = UFO_N_COARSE;
 constexpr int kNS = UFO_N_SAMPLES;

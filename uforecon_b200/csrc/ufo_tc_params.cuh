@@ -18,6 +18,7 @@ struct ViewParams {
   // K' = elu(k) + 1 and V of the view-token row (transformer.py:47, linear_attention.py:36-37 applied to view_token): the same for every
   // sample point, evaluated once on the host from the fp16-rounded operands the QKV GEMM sees (k_view_tc2, fp16 mode)
   float k0[80], v0[80];
+  float vtok_x[80];        // view_token in the channel order of the 16-bit token rows (tok_pos): the token row of the X operand tile
 };
 
 namespace tc {

@@ -191,7 +191,7 @@ k_view_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams 
     const int ln = rr % GR;
     float v[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = (ln < RPW && (ln % L) == 0) ? prm.vtok[c * 8 + k] : 0.f;
+    for (int k = 0; k < 8; ++k) v[k] = (ln < RPW && (ln % L) == 0) ? prm.vtok_x[c * 8 + k] : 0.f;   // token-row order (tok_pos)
     *reinterpret_cast<uint4*>(smem + V2_HALF + hb * V2H_SIZE + V2H_X + c * V2_XLBO + rr * 16) = pack8<BF16>(v);
   }
   umma::fence_async_smem();

@@ -199,7 +199,7 @@ __device__ __forceinline__ void issue_gemm_sub(uint32_t tmem_d, uint32_t a_base,
 // =================================================================================================
 // kernel 2, 16-bit token flavour: same gathers as k_gather, tokens written as the 16-bit operand rows the
 // view-stage kernel loads, pre_sim_mlp (ray_transformer.py:128-132,268) fused in.
-// tok [P][NV][80] 16-bit: [feat 32 | vol 24 | sim 16 | depth-PE 8]
+// tok [P][NV][80] 16-bit, channel c at tok_pos(c) (ufo_common.cuh): [8 x (feat 4 | vol 3 | depth-PE 1) | sim 16]
 // =================================================================================================
 // Per-point buffers of the tensor-core path are laid out [ray][128 slots]: slots 0..63 hold the coarse samples,
 // 64..127 the importance samples, both in evaluation order, so that the fine pass of infer only evaluates the 64
@@ -408,14 +408,12 @@ __global__ void __launch_bounds__(256, UFO_GATHER_MINB) k_gather_tc(SceneDev sc,
       const float4 c = bil_fetch_rgbd(sc.rgbd_cl + n * istride, taps_of(NV + n));
       const float zc = fmaf(sc.w2c_z[n][0], x, fmaf(sc.w2c_z[n][1], y, fmaf(sc.w2c_z[n][2], z, sc.w2c_z[n][3])));
       const float pe = __sinf(fmaf(c.w - zc, fj, pj));                     // ray_transformer.py:66,245 (|arg| < ~40)
-      uint2 f;
+      uint4 f;                                                             // this lane's 16 bytes of the row (tok_pos)
       f.x = umma::pack2<BF16>(ft.x, ft.y);
       f.y = umma::pack2<BF16>(ft.z, ft.w);
-      *reinterpret_cast<uint2*>(row + 4 * j) = f;
-      row[32 + j] = g0;
-      row[40 + j] = g1;
-      row[48 + j] = g2;
-      row[72 + j] = (uint16_t)(umma::pack2<BF16>(pe, 0.f) & 0xffffu);
+      f.z = (uint32_t)g0 | ((uint32_t)g1 << 16);
+      f.w = (uint32_t)g2 | (umma::pack2<BF16>(pe, 0.f) << 16);
+      *reinterpret_cast<uint4*>(row + 8 * j) = f;
       if (j == 0) {
         const float4 pr = my_prj[n];
         const bool inb = (pr.x <= 1.f) && (pr.x >= -1.f) && (pr.y <= 1.f) && (pr.y >= -1.f);
@@ -548,8 +546,8 @@ __global__ void __launch_bounds__(256, UFO_GATHER_MINB) k_gather_tc(SceneDev sc,
             const int n = n0 + tq;
             if (n < NV) {
               uint16_t* row = tok + (sl * NV + n) * kDView;
-              *reinterpret_cast<uint4*>(row + 56) = lo;
-              *reinterpret_cast<uint4*>(row + 64) = hi;
+              *reinterpret_cast<uint4*>(row + 64) = lo;                   // tok_pos(56..71)
+              *reinterpret_cast<uint4*>(row + 72) = hi;
             }
           }
         }
@@ -596,7 +594,7 @@ k_view_tc(const uint8_t* __restrict__ wimg, const __grid_constant__ ViewParams p
     const int rr = i & 127, c = i >> 7;
     float v[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = (c < 10 && rr < ROWS && (rr % L) == 0) ? prm.vtok[c * 8 + k] : 0.f;
+    for (int k = 0; k < 8; ++k) v[k] = (c < 10 && rr < ROWS && (rr % L) == 0) ? prm.vtok_x[c * 8 + k] : 0.f;
     st_chunk<BF16>(smem + V_X, rr, c, v);
   }
   umma::fence_async_smem();
