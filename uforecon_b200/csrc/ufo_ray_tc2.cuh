@@ -38,7 +38,9 @@ constexpr uint32_t R2W_END = R2W_DEN + 2 * 32 * 96 * 2;    // 178,688
 constexpr uint32_t R2_K = 0;                               // K' 11 chunks (MN-major B of the K^T.V product); later KV block-diagonal of sequence 0
 constexpr uint32_t R2_V = R2_K + 11 * kChunk;              // V' 12 chunks, chunk 11 = ones block; later sequence 1; the M = 128 read of the
                                                            // K^T.V product runs 8 KB past it into slot 0 (finite weights, rows never used)
-constexpr uint32_t R2_SCR = R2_V + 96 * 96 * 2;            // LayerNorm / SRDF partials: inside the V' tile, behind the KV operand
+constexpr uint32_t R2_XROW = 336;                           // stash of the fp32 input rows: 320 bytes + 16 of padding (conflict-free 16-byte reads)
+constexpr uint32_t R2_SCR = R2_K + 128 * R2_XROW;          // LayerNorm / SRDF partials: inside the V' tile (chunk 10), behind the KV operand and the stash
+static_assert(R2_SCR >= R2_V + 96 * 96 * 2 && R2_SCR + 2 * 128 * 8 <= R2_V + 11 * kChunk, "scratch must lie between the KV operand and the ones block of V'");
 constexpr uint32_t R2_SLOT = R2_V + 12 * kChunk;           // two weight slots
 constexpr uint32_t R2_SLOT_BYTES = 176 * 96 * 2;           // 33,792: the largest piece
 constexpr uint32_t R2_BAR = R2_SLOT + 2 * R2_SLOT_BYTES;
@@ -116,6 +118,7 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     umma::mbar_init(bar, 1);
     umma::mbar_init(full, 1);
     umma::mbar_init(full + 1, 1);
+    umma::mbar_init(reinterpret_cast<uint64_t*>(smem + R2_BAR + 24), 1);
     umma::fence_barrier_init();
   }
   // the ones block of V' (rows 88..95 of the K^T.V product = sum_s K'_s) never changes
@@ -224,33 +227,39 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
   };
   // This thread's half of the fp32 input row, chunks 6 g .. 6 g + 5: view-stage output (chunks 0..9), order encoding (chunk 10,
   // ray_transformer.py:301-303), zero (chunk 11).  A tile needs it twice (three times with two sequences): as the 16-bit operand of
-  // R0 (and of mlp.0 when x was overwritten in TMEM) and in fp32 as the residual of R12.  It is copied global -> SHARED memory by
-  // cp.async (x_copy) and read from there (x_get): no registers are held while the copy is in flight and no scoreboard of the warp is
-  // tied to it.  As register loads issued "under" an MMA wait (the first version) the warp could not leave that wait before its loads
-  // had landed: measured with per-phase clocks, the two waits that carried the loads took 2180 and 2990 cycles where the others take
-  // 850-1050 (12 % of a tile).  The stash is the K' / V' operand area, dead between the message GEMM (R5) and the next tile's R2a:
-  //   piece j (16 bytes) of thread (r, g = 0): R2_K + j * 2048 + r * 16, j < 12;   (r, g = 1): R2_K + 24576 + j * 2048 + r * 16, j < 8
-  // (ends at R2_SCR; a thread only reads what it copied itself, so cp.async.wait_group is all the synchronisation it needs).
-  static_assert(R2_K + 24576 + 8 * 2048 <= R2_SCR, "x stash overlaps the scratch");
-  const uint32_t xs_u32 = sm_base + R2_K + (g ? 24576u : 0u) + (uint32_t)r * 16u;
-  const float4* const xs_ptr = reinterpret_cast<const float4*>(smem + R2_K + (g ? 24576 : 0) + r * 16);
-  auto x_copy = [&](long long ir) {
-    const bool ok = ir >= 0;
-    const float* src = vout0 + (size_t)(ok ? ir : 0) * kDView + 48 * g;      // chunk 6 g of the row
-    const uint32_t nbytes = ok ? 16u : 0u;                                   // rows past P: zero fill
-#pragma unroll
-    for (int j = 0; j < 12; ++j)
-      if (j < 8 || g == 0)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(xs_u32 + j * 2048u), "l"(src + 4 * j), "r"(nbytes) : "memory");
-    cp_async_commit();
+  // R0 (and of mlp.0 when x was overwritten in TMEM) and in fp32 as the residual of R12.  The 128 rows of a tile (320 bytes each) go
+  // global -> SHARED memory as 128 bulk copies (cp.async.bulk, one per row, issued by the row's g = 0 thread, completing on the mbarrier
+  // xbar) and are read from there (x_get).  History, measured with per-phase clocks (profiles/r02_phase_clocks_*.txt):
+  //   * register loads issued "under" an MMA wait: the warp cannot leave the wait before its loads have landed (shared scoreboards) -
+  //     those two waits took 2180 and 2990 cycles where the others take 850-1050;
+  //   * cp.async (LDGSTS), 12 per thread: no scoreboard, but 3072 LSU operations per pass and CTA at ~8 cycles each, and the next
+  //     barrier drains them - the phases that issued them took 3270 and 2520 cycles (ray stage 166 -> 151 ms all the same);
+  //   * bulk copies run on the copy engine: 128 per pass, nothing for the LSU to drain.
+  // The stash is the K' / V' operand area, dead between the message GEMM (R5) and the next tile's R2a: row r at R2_K + r * 336.
+  uint64_t* xbar = reinterpret_cast<uint64_t*>(smem + R2_BAR + 24);
+  uint32_t xph = 0;                                                          // parity of the next stash completion (every thread)
+  auto x_copy = [&](long long ir, long long tile_of_rows) {
+    const long long left = P - tile_of_rows * 128;                           // rows of that tile inside P: the prefix r < left
+    const uint32_t bytes = (uint32_t)(left < 128 ? left : 128) * 320u;
+    if (wl == 1 && umma::elect_one())
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_u32(xbar)), "r"(bytes) : "memory");
+    if (g == 0 && ir >= 0)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sm_base + R2_K + (uint32_t)r * R2_XROW),
+                   "l"(vout0 + (size_t)ir * kDView), "r"(320u), "r"(umma::smem_u32(xbar))
+                   : "memory");
   };
+  auto x_wait = [&]() {
+    umma::mbar_wait(xbar, xph);
+    xph ^= 1;
+  };
+  const float4* const xs_ptr = reinterpret_cast<const float4*>(smem + R2_K + r * R2_XROW + g * 192);
   float4 xr[12];
-  auto x_get = [&]() {                                                       // after cp_async_wait_all()
+  auto x_get = [&](bool ok) {                                                // after x_wait(); rows past P read as zeros
 #pragma unroll
-    for (int j = 0; j < 8; ++j) xr[j] = xs_ptr[j * 128];
+    for (int j = 0; j < 8; ++j) xr[j] = ok ? xs_ptr[j] : make_float4(0.f, 0.f, 0.f, 0.f);
     if (g == 0) {
 #pragma unroll
-      for (int j = 8; j < 12; ++j) xr[j] = xs_ptr[j * 128];
+      for (int j = 8; j < 12; ++j) xr[j] = ok ? xs_ptr[j] : make_float4(0.f, 0.f, 0.f, 0.f);
     } else {
       const float4* pe = reinterpret_cast<const float4*>(pe_table + (r % SN) * 8);
       xr[8] = __ldg(pe);
@@ -284,7 +293,7 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     }
   };
   long long in_row_cur = (long long)blockIdx.x < n_tiles ? in_row_from(blockIdx.x, perm_load(blockIdx.x)) : -1;
-  if ((long long)blockIdx.x < n_tiles) x_copy(in_row_cur);
+  if ((long long)blockIdx.x < n_tiles) x_copy(in_row_cur, blockIdx.x);
 
 #ifdef UFO_PHASE_TIMING
   // interval k of a tile ends at the k-th UFO_TIM(): even k = a barrier in front of an MMA issue (epilogue + barrier), odd k = the return
@@ -308,8 +317,8 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     const unsigned pv_nx = has_next ? perm_load(tile + gridDim.x) : 0u;         // the next tile's perm byte: used in R13
     if (has_next) x_prefetch(tile + gridDim.x);
     // ---- R0: x = [view-stage token 0 output | order encoding | 0] -> 16-bit A operand in TMEM (chunks 6 g .. 6 g + 5)
-    cp_async_wait_all();                                         // copy issued by the previous tile's R13 (or the prologue)
-    x_get();
+    x_wait();                                                    // copy issued by the previous tile's R13 (or the prologue)
+    x_get(row_ok);
     x_store(C_X, 12);
     umma::tmem_st_wait();
     umma::tc_fence_before();
@@ -450,7 +459,7 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
     }
     mma_wait();
     UFO_TIM();
-    x_copy(in_row);                                              // K' / V' / KV are dead: this tile's x again -> stash (for R8 / R12), an L2 hit
+    x_copy(in_row, tile);                                        // K' / V' / KV are dead: this tile's x again -> stash (for R8 / R12), an L2 hit
     // ---- R6: msg = numerator / (normaliser + 1e-6)                (linear_attention.py:44-45) -> A operand of the merge
     {
       const uint32_t dm = tl + ((NSEQ == 1 || r < SN) ? D_S0 : D_S1);
@@ -507,8 +516,8 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
         umma::tmem_ld_wait();
         red[GG * 128 + r] = ln_partial<NC>(v);
         if (NSEQ > 1) {                                           // x again, for the [LN1 | x] operand
-          cp_async_wait_all();
-          x_get();
+          x_wait();
+          x_get(row_ok);
           x_store(C_XL + 44, 11);
         }
         umma::tc_fence_before();
@@ -623,8 +632,8 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
         red[GG * 128 + r] = ln_partial<NC>(v);
         umma::tc_fence_before();
         pair_sync();
-        cp_async_wait_all();
-        x_get();                                                   // fp32 input row from the stash (copied at R6)
+        if (NSEQ == 1) x_wait();                                   // (with two sequences R8 has waited for this copy)
+        x_get(row_ok);                                             // fp32 input row from the stash (copied at R6)
         const float2 st = ln2_stats(red, r, 1.f / 88.f);
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
@@ -672,7 +681,7 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
       }
     }
     const long long in_row_nx = has_next ? in_row_from(tile + gridDim.x, pv_nx) : -1;
-    if (has_next) x_copy(in_row_nx);                             // the next tile's x: under the SRDF-head GEMM and its tail
+    if (has_next) x_copy(in_row_nx, tile + gridDim.x);           // the next tile's x: under the SRDF-head GEMM and its tail
     in_row_cur = in_row_nx;
     mma_wait();
     UFO_TIM();
@@ -704,13 +713,14 @@ k_ray_tc2(const uint8_t* __restrict__ wimg, const __grid_constant__ RayParams pr
       pair_sync();
       if (g == 0 && row_ok) srdf[prow] = prm.db4 + (part_s[r] + part_s[128 + r]);
     }
+    UFO_TIM();                                                   // interval 18: the SRDF-head tail (R14)
     // the scratch is rewritten by the next tile's R2a only after its R0 barrier; TMEM is rewritten after that barrier too
   }
 #ifdef UFO_PHASE_TIMING
   if (blockIdx.x == 0 && t == 32 && n_tiles >= 4096) {
     const unsigned long long nt = (unsigned long long)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
     printf("RAYTIM SN=%d tiles=%llu :", SN, nt);
-    for (int i = 0; i < 18; ++i) printf(" %llu", tim[i] / nt);
+    for (int i = 0; i < 19; ++i) printf(" %llu", tim[i] / nt);
     printf("\n");
   }
 #endif
