@@ -738,8 +738,8 @@ def roofline_entries(prof, args, n_rays, pk):
             extra["tap_bytes_per_launch"] = tap / cnt
             if t:
                 work = t["bytes_per_launch"] * cnt
-                note = ("achieved = DRAM bytes the launch moves (ncu, same chunk size: 70 % of them are the token / colour / direction "
-                        "rows it writes for the view stage) / live launch time; the limiter is L1 + issue, not HBM: see tap_gbs "
+                note = ("achieved = DRAM bytes the launch moves (ncu, same chunk size: the scene tensors it reads and the token / colour / "
+                        "direction rows it writes for the view stage - 28 % of the bytes in the coarse pass, 85 % in the fine pass) / live launch time; the limiter is L1 + issue, not HBM: see tap_gbs "
                         "(texel / voxel tap bytes pulled through L1) and the ncu utilisations")
             else:
                 # no ncu capture at this view count / size: a lower bound of the launch's DRAM traffic that follows from the
