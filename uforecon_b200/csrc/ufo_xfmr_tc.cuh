@@ -285,7 +285,17 @@ __device__ __forceinline__ BilTaps bil_setup_rt(float u, float v, int H, int W, 
 }
 
 // shared-memory bytes of k_gather_tc<NV>: pre_sim_mlp weights, similarity staging, per-round projections and taps
-constexpr int kGatherWFloats = 8 * 32 + 32 + 32 * 32 + 32 + 32 * 16 + 16 + 16;   // + pad to a 16-byte multiple
+// -DUFO_GATHER_SMEM2: bank-conflict-free shared-memory layout of k_gather_tc.  ncu (v38, source page) counts 5.5 wavefronts per LDS.64
+// where 2 are ideal (the pre_sim weight fragments: rows of 32 floats put the eight rows a warp reads together into the same banks) and 5.6
+// per STS.128 where 2.4 are ideal (the tap records: lane j writes 32 bytes at a 32-byte stride, lanes j and j + 4 collide) - 23 M of the
+// kernel's 70 M shared-memory wavefronts, on the pipe that bounds it.  With the flag the weight rows are 40 floats apart and a point's tap
+// records are two planes (indices | weights) that the eight lanes write as consecutive 16-byte pieces.  Same values, same order of operations.
+#ifdef UFO_GATHER_SMEM2
+constexpr int kGatherWRow = 40;
+#else
+constexpr int kGatherWRow = 32;
+#endif
+constexpr int kGatherWFloats = 8 * 32 + 32 + 32 * kGatherWRow + 32 + 16 * kGatherWRow + 16 + 16;   // + pad to a 16-byte multiple
 template <int NV>
 constexpr int gather_tc_smem() { return kGatherWFloats * 4 + 256 * 9 * 4 + 32 * NV * 16 + 32 * 3 * NV * 32; }
 
@@ -309,13 +319,14 @@ __global__ void __launch_bounds__(256, UFO_GATHER_MINB) k_gather_tc(SceneDev sc,
   float(*s_sim)[9] = reinterpret_cast<float(*)[9]>(gsm + kGatherWFloats * 4);
   float4* s_prj = reinterpret_cast<float4*>(gsm + kGatherWFloats * 4 + 256 * 9 * 4);
   uint4* s_tap = reinterpret_cast<uint4*>(gsm + kGatherWFloats * 4 + 256 * 9 * 4 + 32 * NV * 16);
-  constexpr int o_b0 = 8 * 32, o_w2 = o_b0 + 32, o_b2 = o_w2 + 32 * 32, o_w4 = o_b2 + 32, o_b4 = o_w4 + 32 * 16;
+  constexpr int WR = kGatherWRow;
+  constexpr int o_b0 = 8 * 32, o_w2 = o_b0 + 32, o_b2 = o_w2 + 32 * WR, o_w4 = o_b2 + 32, o_b4 = o_w4 + 16 * WR;
   {  // pre_sim_mlp weights -> shared memory
     for (int i = threadIdx.x; i < 8 * 32; i += 256) s_w[i] = __ldg(presim.w0 + i);
     for (int i = threadIdx.x; i < 32; i += 256) s_w[o_b0 + i] = __ldg(presim.b0 + i);
-    for (int i = threadIdx.x; i < 32 * 32; i += 256) s_w[o_w2 + i] = __ldg(presim.w2 + i);
+    for (int i = threadIdx.x; i < 32 * 32; i += 256) s_w[o_w2 + (i >> 5) * WR + (i & 31)] = __ldg(presim.w2 + i);
     for (int i = threadIdx.x; i < 32; i += 256) s_w[o_b2 + i] = __ldg(presim.b2 + i);
-    for (int i = threadIdx.x; i < 32 * 16; i += 256) s_w[o_w4 + i] = __ldg(presim.w4 + i);
+    for (int i = threadIdx.x; i < 32 * 16; i += 256) s_w[o_w4 + (i >> 5) * WR + (i & 31)] = __ldg(presim.w4 + i);
     for (int i = threadIdx.x; i < 16; i += 256) s_w[o_b4 + i] = __ldg(presim.b4 + i);
   }
   __syncthreads();        // the weights are read after the gather rounds, which end in a warp-level barrier only (below)
@@ -327,6 +338,11 @@ __global__ void __launch_bounds__(256, UFO_GATHER_MINB) k_gather_tc(SceneDev sc,
   const size_t fstride = (size_t)sc.h * sc.w * kFeatC, istride = (size_t)sc.H * sc.W;
   float4* my_prj = s_prj + sub * NV;
   uint4* my_tap = s_tap + sub * (3 * NV) * 2;
+#ifdef UFO_GATHER_SMEM2
+  constexpr int kTapI = 1, kTapW = 3 * NV;      // record k of a point: indices at [k], weights at [3 NV + k]
+#else
+  constexpr int kTapI = 2, kTapW = 1;           // indices at [2 k], weights at [2 k + 1]
+#endif
   for (int round = 0; round < 8; ++round) {
     const long long p = p0 + round * 32 + sub;
     if (p >= P) break;
@@ -349,13 +365,13 @@ __global__ void __launch_bounds__(256, UFO_GATHER_MINB) k_gather_tc(SceneDev sc,
         if (kind == 0) my_prj[n] = make_float4(u, v, qz, 0.f);
         const bool big = (kind == 1);
         const BilTaps t = bil_setup_rt(u, v, big ? sc.H : sc.h, big ? sc.W : sc.w, kind == 2, kind == 2);
-        my_tap[2 * k] = make_uint4((unsigned)t.i00, (unsigned)t.i01, (unsigned)t.i10, (unsigned)t.i11);
-        my_tap[2 * k + 1] = make_uint4(__float_as_uint(t.w00), __float_as_uint(t.w01), __float_as_uint(t.w10), __float_as_uint(t.w11));
+        my_tap[kTapI * k] = make_uint4((unsigned)t.i00, (unsigned)t.i01, (unsigned)t.i10, (unsigned)t.i11);
+        my_tap[kTapI * k + kTapW] = make_uint4(__float_as_uint(t.w00), __float_as_uint(t.w01), __float_as_uint(t.w10), __float_as_uint(t.w11));
       }
     }
     __syncwarp(gmask);
     auto taps_of = [&](int k) {
-      const uint4 a = my_tap[2 * k], b = my_tap[2 * k + 1];
+      const uint4 a = my_tap[kTapI * k], b = my_tap[kTapI * k + kTapW];
       BilTaps t;
       t.i00 = (int)a.x; t.i01 = (int)a.y; t.i10 = (int)a.z; t.i11 = (int)a.w;
       t.w00 = __uint_as_float(b.x); t.w01 = __uint_as_float(b.y); t.w10 = __uint_as_float(b.z); t.w11 = __uint_as_float(b.w);
@@ -470,7 +486,7 @@ __global__ void __launch_bounds__(256, UFO_GATHER_MINB) k_gather_tc(SceneDev sc,
       w0f[nt] = pk(s_w[n * 8 + 2 * tq], s_w[n * 8 + 2 * tq + 1]);
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
-        const float* w = s_w + o_w2 + n * 32 + 16 * ks + 2 * tq;
+        const float* w = s_w + o_w2 + n * WR + 16 * ks + 2 * tq;
         w2f[ks][nt][0] = pk(w[0], w[1]);
         w2f[ks][nt][1] = pk(w[8], w[9]);
       }
@@ -479,7 +495,7 @@ __global__ void __launch_bounds__(256, UFO_GATHER_MINB) k_gather_tc(SceneDev sc,
     for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
-        const float* w = s_w + o_w4 + (gq + 8 * nt) * 32 + 16 * ks + 2 * tq;
+        const float* w = s_w + o_w4 + (gq + 8 * nt) * WR + 16 * ks + 2 * tq;
         w4f[ks][nt][0] = pk(w[0], w[1]);
         w4f[ks][nt][1] = pk(w[8], w[9]);
       }
